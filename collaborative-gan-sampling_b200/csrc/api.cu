@@ -1,0 +1,30 @@
+// Library-level entry points: version, thread-local error string, device gate.
+#include "common.h"
+
+namespace cgs {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int require_sm100() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_ok = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "no CUDA device: %s (libcgs has no CPU path)", cudaGetErrorString(e));
+  if (dev == cached_dev && cached_ok) return CGS_OK;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (major != 10) return set_error(CGS_ERR_CUDA, "libcgs is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+  cached_dev = dev;
+  cached_ok = 1;
+  return CGS_OK;
+}
+
+}  // namespace cgs
+
+extern "C" int cgs_version(void) { return CGS_ABI_VERSION; }
+extern "C" const char* cgs_last_error(void) { return cgs::error_buffer(); }

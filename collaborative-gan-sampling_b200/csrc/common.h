@@ -1,0 +1,30 @@
+// Shared host-side helpers: status codes, thread-local error message, CUDA error capture.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "cgs.h"
+
+namespace cgs {
+
+char* error_buffer();   // thread-local, 512 bytes (api.cu)
+
+inline int set_error(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return CGS_OK;
+}
+
+// The product never runs on anything but sm_100: refuse loudly instead of falling back.
+int require_sm100();
+
+}  // namespace cgs

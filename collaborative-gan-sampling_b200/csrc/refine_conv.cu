@@ -1,0 +1,636 @@
+// Image-path refinement: layer -> gathered-GEMM parameter mapping, the fused head kernel (logit GEMV +
+// BCE gradient + best-of-K select + image keep), and the K-step loop of sampling/collaborator.py:41-88.
+#include "common.h"
+#include "conv_gemm.cuh"
+
+#include <cstring>
+
+namespace cgs {
+
+namespace {
+
+inline int cstride(int c) { return (c + 3) & ~3; }   // NHWC channel stride (floats)
+
+inline int same_pad_before(int in_size, int k) {      // TF SAME, stride 2
+  const int out = (in_size + 1) / 2;
+  int total = (out - 1) * 2 + k - in_size;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+struct LayerShape {
+  int hout, wout, cs_in, cs_out;
+};
+
+LayerShape layer_shape(const cgs_layer_desc& L) {
+  LayerShape s;
+  s.cs_in = cstride(L.cin);
+  s.cs_out = cstride(L.cout);
+  if (L.type == CGS_LAYER_CONV) {
+    s.hout = (L.hin + 1) / 2;
+    s.wout = (L.win + 1) / 2;
+  } else if (L.type == CGS_LAYER_DECONV) {
+    s.hout = L.hin * 2;
+    s.wout = L.win * 2;
+  } else {
+    s.hout = s.wout = 1;
+  }
+  return s;
+}
+
+int check_layer(const cgs_layer_desc& L) {
+  if (L.type == CGS_LAYER_FC) {
+    if (L.cin % 32) return set_error(CGS_ERR_UNSUPPORTED, "fc input size %d must be a multiple of 32", L.cin);
+    return CGS_OK;
+  }
+  if (L.k < 2 || L.k > 5) return set_error(CGS_ERR_UNSUPPORTED, "kernel size %d unsupported (2..5)", L.k);
+  if ((L.hin & 1) && L.type == CGS_LAYER_CONV)
+    return set_error(CGS_ERR_UNSUPPORTED, "odd conv input size %d unsupported", L.hin);
+  const bool in_ok = (L.cin % 32 == 0) || L.cin <= 4;
+  const bool out_ok = (L.cout % 32 == 0) || L.cout <= 4;
+  if (!in_ok || !out_ok)
+    return set_error(CGS_ERR_UNSUPPORTED, "channels (%d -> %d) must be <= 4 or multiples of 32", L.cin, L.cout);
+  // the transposed-type pass gathers 32-channel blocks of its input
+  if (L.type == CGS_LAYER_DECONV && L.cin % 32) return set_error(CGS_ERR_UNSUPPORTED, "deconv cin %d", L.cin);
+  if (L.type == CGS_LAYER_CONV && L.cout % 32) return set_error(CGS_ERR_UNSUPPORTED, "conv cout %d", L.cout);
+  return CGS_OK;
+}
+
+// Strided-type pass ("F"): out pixel (j,i) reads in pixels (2j+ky-p, 2i+kx-p); K order (ky,kx,c).
+void fill_strided(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) {
+  p.nclasses = 1;
+  GemmClass& g = p.cls[0];
+  g.k0 = 0;
+  g.oy0 = g.ox0 = 0;
+  g.ntaps = k * k;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      g.dy[ky * k + kx] = (signed char)(ky - pad_y);
+      g.dx[ky * k + kx] = (signed char)(kx - pad_x);
+    }
+  if (cin_k % 32 == 0) {
+    p.cblocks = cin_k / 32;
+    g.nkb = g.ntaps * p.cblocks;
+  } else {
+    p.cblocks = 0;                          // pixel mode: 8 taps x 4 channels per K block
+    g.nkb = (g.ntaps + 7) / 8;
+  }
+  p.S = 2;
+  p.os = 1;
+}
+
+// Transposed-type pass ("T"): output pixel (2j+py, 2i+px) reads in pixels (j+dy, i+dx),
+// dy = (py + p - ky)/2 over the ky with matching parity; K order (class, tap, c).  Classes are emitted
+// heaviest first so the persistent tile loop tails off on the short ones.
+void fill_transposed(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) {
+  p.nclasses = 4;
+  p.cblocks = cin_k / 32;
+  p.S = 1;
+  p.os = 2;
+  int k0 = 0;
+  int ci = 0;
+  // order parities by tap count (descending)
+  int py_order[2] = {0, 1}, px_order[2] = {0, 1};
+  auto ntap = [&](int par, int pad) { int n = 0; for (int kk = 0; kk < k; ++kk) if (((par + pad - kk) & 1) == 0) ++n; return n; };
+  if (ntap(1, pad_y) > ntap(0, pad_y)) { py_order[0] = 1; py_order[1] = 0; }
+  if (ntap(1, pad_x) > ntap(0, pad_x)) { px_order[0] = 1; px_order[1] = 0; }
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int py = py_order[a], px = px_order[b];
+      GemmClass& g = p.cls[ci++];
+      g.k0 = k0;
+      g.oy0 = py;
+      g.ox0 = px;
+      int t = 0;
+      for (int ky = 0; ky < k; ++ky) {
+        if ((py + pad_y - ky) & 1) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          if ((px + pad_x - kx) & 1) continue;
+          g.dy[t] = (signed char)((py + pad_y - ky) / 2);
+          g.dx[t] = (signed char)((px + pad_x - kx) / 2);
+          ++t;
+        }
+      }
+      g.ntaps = t;
+      g.nkb = t * p.cblocks;
+      k0 += t * cin_k;
+    }
+}
+
+}  // namespace
+
+// Parameters of the forward pass of one layer.
+int make_forward_params(const cgs_layer_desc& L, int64_t B, const float* x, float* y, ConvGemmParams& p) {
+  if (int rc = check_layer(L)) return rc;
+  std::memset(&p, 0, sizeof(p));
+  const LayerShape s = layer_shape(L);
+  p.in = x;
+  p.out = y;
+  p.bias = L.bias;
+  p.epi = EPI_FWD;
+  p.act = L.act;
+  p.N = L.cout;
+  p.ON = s.cs_out;
+  p.OH = s.hout;
+  p.OW = s.wout;
+  p.IH = L.hin;
+  p.IW = L.win;
+  p.Cs = s.cs_in;
+  if (L.type == CGS_LAYER_CONV) {
+    fill_strided(p, L.k, same_pad_before(L.hin, L.k), same_pad_before(L.win, L.k), s.cs_in);
+    p.MH = s.hout;
+    p.MW = s.wout;
+  } else if (L.type == CGS_LAYER_DECONV) {
+    fill_transposed(p, L.k, same_pad_before(s.hout, L.k), same_pad_before(s.wout, L.k), L.cin);
+    p.MH = L.hin;
+    p.MW = L.win;
+  } else {
+    p.nclasses = 1;
+    p.cls[0].ntaps = 1;
+    p.cblocks = L.cin / 32;
+    p.cls[0].nkb = p.cblocks;
+    p.S = 1;
+    p.os = 1;
+    p.MH = p.MW = 1;
+    p.IH = p.IW = 1;
+    p.Cs = L.cin;
+  }
+  p.M = (int)(B * p.MH * p.MW);
+  return CGS_OK;
+}
+
+// Parameters of the data-gradient pass of one layer: dy (grad w.r.t. the layer's pre-activation output) -> dx.
+int make_backward_params(const cgs_layer_desc& L, int64_t B, const float* dy, float* dx, ConvGemmParams& p) {
+  if (int rc = check_layer(L)) return rc;
+  std::memset(&p, 0, sizeof(p));
+  const LayerShape s = layer_shape(L);
+  p.in = dy;
+  p.out = dx;
+  p.epi = EPI_RAW;
+  p.N = L.cin;
+  p.ON = s.cs_in;
+  p.OH = L.hin;
+  p.OW = L.win;
+  p.IH = s.hout;
+  p.IW = s.wout;
+  p.Cs = s.cs_out;
+  if (L.type == CGS_LAYER_CONV) {
+    // conv data-gradient is a transposed-type pass over dy
+    fill_transposed(p, L.k, same_pad_before(L.hin, L.k), same_pad_before(L.win, L.k), L.cout);
+    p.MH = s.hout;
+    p.MW = s.wout;
+  } else if (L.type == CGS_LAYER_DECONV) {
+    // deconv data-gradient is a strided-type pass over dy (== conv fprop with the same filter)
+    fill_strided(p, L.k, same_pad_before(s.hout, L.k), same_pad_before(s.wout, L.k), s.cs_out);
+    p.MH = L.hin;
+    p.MW = L.win;
+  } else {
+    if (L.cout % 32) return set_error(CGS_ERR_UNSUPPORTED, "fc output size %d must be a multiple of 32", L.cout);
+    p.nclasses = 1;
+    p.cls[0].ntaps = 1;
+    p.cblocks = L.cout / 32;
+    p.cls[0].nkb = p.cblocks;
+    p.S = 1;
+    p.os = 1;
+    p.MH = p.MW = 1;
+    p.IH = p.IW = 1;
+    p.OH = p.OW = 1;
+    p.Cs = L.cout;
+    p.ON = L.cin;
+  }
+  p.M = (int)(B * p.MH * p.MW);
+  return CGS_OK;
+}
+
+int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int math, cudaStream_t stream) {
+  if (math == CGS_MATH_FP32_SIMT) return launch_conv_gemm_simt(p, w, rows, cols, stream);
+  if (math == CGS_MATH_TF32_TENSOR) return launch_conv_gemm_tc(p, w, rows, cols, stream);
+  return set_error(CGS_ERR_INVALID, "unknown math mode %d", math);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head kernel: final linear (-> 1 logit), BCE-with-ones gradient, selection, image keep.
+//   logit_b = <feat_b, w> + bias                                   (nsgan/ops.py:81, GAN.py:68)
+//   d pre_k = (sigmoid(logit_b) - 1) * w_k * act'(feat_bk)         (GAN.py:176-177, collaborator.py:30-31)
+//   deterministic: update iff logit > best (strict)                (collaborator.py:79-83)
+//   probabilistic: update iff prob_indices[b] == step_index        (collaborator.py:77)
+// One CTA per sample; the dot product is reduced in a fixed order that depends only on K (never on B).
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* feat;    // [B, K]  output of the last hidden layer (post activation)
+  const float* w;       // [K]
+  const float* bias;    // [1] device scalar (folded)
+  int K;
+  int act;              // activation of the producer of feat
+  float* dpre;          // [B, K] or nullptr (no backward wanted)
+  const float* img;     // [B, img_elems] current image
+  float* best_img;      // [B, img_elems]
+  const float* feature; // [B, feat_elems] current feature (only if best_feature wanted)
+  float* best_feature;
+  int img_elems, feat_elems;
+  float* cur_logit;     // [B]
+  float* best_logit;    // [B]
+  float* best_step;     // [B]
+  float* default_logit; // [B] or nullptr
+  const int* prob_indices;
+  int step;             // -1 = initial evaluation (collaborator.py:49-60), else loop index i
+  int mode;
+  unsigned char* done;  // early-exit flags [B] or nullptr
+  float exit_logit;
+};
+
+__global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  __shared__ float red[8];
+  __shared__ float s_logit;
+  __shared__ int s_update;
+  const int b = blockIdx.x;
+  const float* f = p.feat + (size_t)b * p.K;
+  float acc = 0.f;
+  for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(f + k);
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
+    acc = fmaf(a.x, ww.x, acc);
+    acc = fmaf(a.y, ww.y, acc);
+    acc = fmaf(a.z, ww.z, acc);
+    acc = fmaf(a.w, ww.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float logit = t + (p.bias ? __ldg(p.bias) : 0.f);
+    s_logit = logit;
+    p.cur_logit[b] = logit;
+    int upd;
+    if (p.step < 0) {
+      upd = 1;
+      p.best_logit[b] = logit;
+      p.best_step[b] = 1.0f;                                   // collaborator.py:60 (sic)
+      if (p.default_logit) p.default_logit[b] = logit;         // collaborator.py:52
+    } else {
+      const bool frozen = p.done && p.done[b];
+      if (p.mode == CGS_MODE_PROBABILISTIC) upd = (p.prob_indices[b] == p.step);
+      else upd = logit > p.best_logit[b];
+      if (frozen) upd = 0;
+      if (upd) {
+        p.best_logit[b] = logit;
+        p.best_step[b] = (float)(p.step + 1);
+      }
+    }
+    if (p.done && !p.done[b] && logit >= p.exit_logit) p.done[b] = 1;
+    s_update = upd;
+  }
+  __syncthreads();
+  const float logit = s_logit;
+  if (p.dpre) {
+    // d softplus(-l)/dl = sigmoid(l) - 1
+    const float dl = 1.f / (1.f + expf(-logit)) - 1.f;
+    float* d = p.dpre + (size_t)b * p.K;
+    for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
+      const float4 a = *reinterpret_cast<const float4*>(f + k);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
+      float4 o;
+      o.x = dl * ww.x * act_grad_from_output(a.x, p.act);
+      o.y = dl * ww.y * act_grad_from_output(a.y, p.act);
+      o.z = dl * ww.z * act_grad_from_output(a.z, p.act);
+      o.w = dl * ww.w * act_grad_from_output(a.w, p.act);
+      *reinterpret_cast<float4*>(d + k) = o;
+    }
+  }
+  if (s_update) {
+    const float4* src = reinterpret_cast<const float4*>(p.img + (size_t)b * p.img_elems);
+    float4* dst = reinterpret_cast<float4*>(p.best_img + (size_t)b * p.img_elems);
+    for (int i = threadIdx.x; i < p.img_elems / 4; i += 256) dst[i] = src[i];
+    if (p.best_feature) {
+      const float4* fs = reinterpret_cast<const float4*>(p.feature + (size_t)b * p.feat_elems);
+      float4* fd = reinterpret_cast<float4*>(p.best_feature + (size_t)b * p.feat_elems);
+      for (int i = threadIdx.x; i < p.feat_elems / 4; i += 256) fd[i] = fs[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain executor
+// ---------------------------------------------------------------------------------------------
+struct Chain {
+  int n;                         // GEMM layers (G-tail + D without the 1-logit head)
+  cgs_layer_desc layers[2 * CGS_MAX_LAYERS];
+  size_t act_elems[2 * CGS_MAX_LAYERS + 1];   // per-sample elements of act[i] (act[0] = feature)
+  int n_gtail;
+  cgs_layer_desc head;
+  size_t max_elems;
+};
+
+static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& c) {
+  if (!gtail || !d) return set_error(CGS_ERR_INVALID, "null network descriptor");
+  if (gtail->n_layers < 1 || gtail->n_layers > CGS_MAX_LAYERS || d->n_layers < 2 || d->n_layers > CGS_MAX_LAYERS)
+    return set_error(CGS_ERR_INVALID, "bad layer counts (%d, %d)", gtail->n_layers, d->n_layers);
+  c.n = 0;
+  for (int i = 0; i < gtail->n_layers; ++i) c.layers[c.n++] = gtail->layers[i];
+  c.n_gtail = gtail->n_layers;
+  for (int i = 0; i < d->n_layers - 1; ++i) c.layers[c.n++] = d->layers[i];
+  c.head = d->layers[d->n_layers - 1];
+  if (c.head.type != CGS_LAYER_FC || c.head.cout != 1)
+    return set_error(CGS_ERR_UNSUPPORTED, "discriminator must end in a linear layer with one logit");
+  const cgs_layer_desc& L0 = c.layers[0];
+  c.act_elems[0] = (size_t)L0.hin * L0.win * cstride(L0.cin);
+  c.max_elems = c.act_elems[0];
+  for (int i = 0; i < c.n; ++i) {
+    if (int rc = check_layer(c.layers[i])) return rc;
+    const LayerShape s = layer_shape(c.layers[i]);
+    c.act_elems[i + 1] = (size_t)s.hout * s.wout * s.cs_out;
+    if (c.act_elems[i + 1] > c.max_elems) c.max_elems = c.act_elems[i + 1];
+    if (i + 1 < c.n) {
+      const cgs_layer_desc& Ln = c.layers[i + 1];
+      const size_t expect = (Ln.type == CGS_LAYER_FC) ? (size_t)Ln.cin : (size_t)Ln.hin * Ln.win * cstride(Ln.cin);
+      if (expect != c.act_elems[i + 1])
+        return set_error(CGS_ERR_INVALID, "layer %d output (%zu) does not feed layer %d input (%zu)", i,
+                         c.act_elems[i + 1], i + 1, expect);
+    }
+  }
+  if ((size_t)c.head.cin != c.act_elems[c.n]) return set_error(CGS_ERR_INVALID, "head input size mismatch");
+  if (c.head.cin % 4) return set_error(CGS_ERR_UNSUPPORTED, "head input size must be a multiple of 4");
+  return CGS_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Workspace {
+  float* act[2 * CGS_MAX_LAYERS + 1];
+  float* g[2];
+  float* mom;
+  float* cur_logit;
+  unsigned char* done;
+  size_t total;
+};
+
+// act[0] is the caller's feature buffer; everything else is carved out of the workspace.
+static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align256(bytes); return p; };
+  w.act[0] = nullptr;
+  for (int i = 1; i <= c.n; ++i) w.act[i] = (float*)take((size_t)B * c.act_elems[i] * 4);
+  w.g[0] = (float*)take((size_t)B * c.max_elems * 4);
+  w.g[1] = (float*)take((size_t)B * c.max_elems * 4);
+  w.mom = (float*)take((size_t)B * c.act_elems[0] * 4);
+  w.cur_logit = (float*)take((size_t)B * 4);
+  w.done = (unsigned char*)take((size_t)B);
+  w.total = off;
+}
+
+static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st) {
+  for (int i = 0; i < c.n; ++i) {
+    ConvGemmParams p;
+    if (int rc = make_forward_params(c.layers[i], B, w.act[i], w.act[i + 1], p)) return rc;
+    if (int rc = launch_gemm(p, c.layers[i].w_fwd, c.layers[i].rows_fwd, c.layers[i].kcols_fwd, math, st)) return rc;
+  }
+  return CGS_OK;
+}
+
+// Backward from dpre[c.n-1] (already in w.g[0]) down to the feature.  `upd` != null fuses the policy step into
+// the last GEMM's epilogue; otherwise the raw gradient is written to grad_out.
+static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math, const ConvGemmParams* upd,
+                        float* grad_out, cudaStream_t st) {
+  int cur = 0;
+  for (int i = c.n - 1; i >= 0; --i) {
+    ConvGemmParams p;
+    float* dst = (i == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
+    if (int rc = make_backward_params(c.layers[i], B, w.g[cur], dst, p)) return rc;
+    if (i > 0) {
+      p.epi = EPI_BWD;
+      p.aux = w.act[i];
+      p.act = c.layers[i - 1].act;
+    } else if (upd) {
+      p.epi = EPI_UPDATE;
+      p.mom = upd->mom;
+      p.first = upd->first;
+      p.sgd = upd->sgd;
+      p.rate = upd->rate;
+      p.alpha = upd->alpha;
+      p.clip = upd->clip;
+      p.vmin = upd->vmin;
+      p.vmax = upd->vmax;
+    }
+    if (int rc = launch_gemm(p, c.layers[i].w_bwd, c.layers[i].rows_bwd, c.layers[i].kcols_bwd, math, st)) return rc;
+    cur ^= 1;
+  }
+  return CGS_OK;
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" size_t cgs_refine_workspace_bytes(const cgs_net_desc* gtail, const cgs_net_desc* d, int64_t B) {
+  Chain c;
+  if (build_chain(gtail, d, c) != CGS_OK || B < 0) return 0;
+  Workspace w;
+  carve(c, B, nullptr, w);
+  return w.total + 256;
+}
+
+static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams hp, cudaStream_t st) {
+  hp.feat = w.act[c.n];
+  hp.w = c.head.w_fwd;
+  hp.bias = c.head.bias;
+  hp.K = c.head.cin;
+  hp.act = c.layers[c.n - 1].act;
+  hp.img = w.act[c.n_gtail];
+  hp.img_elems = (int)c.act_elems[c.n_gtail];
+  hp.feature = w.act[0];
+  hp.feat_elems = (int)c.act_elems[0];
+  hp.cur_logit = w.cur_logit;
+  head_kernel<<<(unsigned)B, 256, 0, st>>>(hp);
+  return check_launch("head_kernel");
+}
+
+extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d, const cgs_refine_cfg* cfg,
+                               int64_t B, float* feature, float* best_img, float* best_logit, float* best_step,
+                               float* default_logit, const int32_t* prob_indices, float* best_feature,
+                               void* workspace, size_t workspace_bytes, cgs_stream_t stream) {
+  if (int rc = require_sm100()) return rc;
+  if (!cfg || !feature || !best_img || !best_logit || !best_step) return set_error(CGS_ERR_INVALID, "null argument");
+  if (B <= 0) return B == 0 ? CGS_OK : set_error(CGS_ERR_INVALID, "negative batch");
+  if (cfg->method != CGS_POLICY_SGD && cfg->method != CGS_POLICY_MOMENTUM)
+    return set_error(CGS_ERR_UNSUPPORTED, "graph refiner supports sgd / momentum only (sampling/policy.py:51)");
+  if (cfg->mode == CGS_MODE_PROBABILISTIC && !prob_indices)
+    return set_error(CGS_ERR_INVALID, "probabilistic mode needs prob_indices");
+  if (cfg->mode != CGS_MODE_PROBABILISTIC && cfg->mode != CGS_MODE_DETERMINISTIC)
+    return set_error(CGS_ERR_UNSUPPORTED, "unknown mode %d", cfg->mode);
+  Chain c;
+  if (int rc = build_chain(gtail, d, c)) return rc;
+  Workspace w;
+  carve(c, B, (void*)(((uintptr_t)workspace + 255) & ~uintptr_t(255)), w);
+  if (!workspace || w.total + 256 > workspace_bytes) return set_error(CGS_ERR_WORKSPACE, "workspace too small");
+  if ((long long)B * (long long)c.max_elems >= (1ll << 31))
+    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split the batch");
+  w.act[0] = feature;
+  cudaStream_t st = (cudaStream_t)stream;
+  HeadParams hp;
+  std::memset(&hp, 0, sizeof(hp));
+  hp.best_img = best_img;
+  hp.best_logit = best_logit;
+  hp.best_step = best_step;
+  hp.default_logit = default_logit;
+  hp.best_feature = best_feature;
+  hp.prob_indices = prob_indices;
+  hp.mode = cfg->mode;
+  hp.exit_logit = cfg->exit_logit;
+  if (cfg->early_exit) {
+    hp.done = w.done;
+    cudaMemsetAsync(w.done, 0, (size_t)B, st);
+  }
+  const int K = cfg->steps;
+  // initial evaluation: collaborator.py:48-60
+  if (int rc = run_forward(c, w, B, cfg->math, st)) return rc;
+  hp.step = -1;
+  hp.dpre = K > 0 ? w.g[0] : nullptr;
+  if (int rc = head_launch(c, w, B, hp, st)) return rc;
+  ConvGemmParams upd;
+  std::memset(&upd, 0, sizeof(upd));
+  upd.mom = w.mom;
+  upd.sgd = cfg->method == CGS_POLICY_SGD;
+  upd.rate = cfg->rate;
+  upd.alpha = cfg->alpha;
+  upd.clip = cfg->clip;
+  upd.vmin = cfg->vmin;
+  upd.vmax = cfg->vmax;
+  for (int i = 0; i < K; ++i) {                       // collaborator.py:63-83
+    upd.first = (i == 0);
+    if (int rc = run_backward(c, w, B, cfg->math, &upd, nullptr, st)) return rc;   // grad + policy step (:66-70)
+    if (int rc = run_forward(c, w, B, cfg->math, st)) return rc;                   // :73
+    hp.step = i;
+    hp.dpre = (i + 1 < K) ? w.g[0] : nullptr;         // the gradient after the last step is never consumed
+    if (int rc = head_launch(c, w, B, hp, st)) return rc;                          // :76-83
+  }
+  return CGS_OK;
+}
+
+extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_net_desc* d, int math, int64_t B,
+                                           const float* feature, float* logit_out, float* grad_out, float* img_out,
+                                           void* workspace, size_t workspace_bytes, cgs_stream_t stream) {
+  if (int rc = require_sm100()) return rc;
+  if (!feature || !logit_out) return set_error(CGS_ERR_INVALID, "null argument");
+  if (B <= 0) return B == 0 ? CGS_OK : set_error(CGS_ERR_INVALID, "negative batch");
+  Chain c;
+  if (int rc = build_chain(gtail, d, c)) return rc;
+  Workspace w;
+  carve(c, B, (void*)(((uintptr_t)workspace + 255) & ~uintptr_t(255)), w);
+  if (!workspace || w.total + 256 > workspace_bytes) return set_error(CGS_ERR_WORKSPACE, "workspace too small");
+  if ((long long)B * (long long)c.max_elems >= (1ll << 31))
+    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split the batch");
+  w.act[0] = const_cast<float*>(feature);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = run_forward(c, w, B, math, st)) return rc;
+  HeadParams hp;
+  std::memset(&hp, 0, sizeof(hp));
+  // selection outputs are not wanted here: point them at scratch so the kernel stays branch-free
+  hp.best_img = w.g[1];
+  hp.best_logit = w.cur_logit;
+  hp.best_step = w.mom;          // scratch (>= B floats)
+  hp.step = -1;
+  hp.dpre = grad_out ? w.g[0] : nullptr;
+  if (int rc = head_launch(c, w, B, hp, st)) return rc;
+  cudaMemcpyAsync(logit_out, w.cur_logit, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
+  if (img_out)
+    cudaMemcpyAsync(img_out, w.act[c.n_gtail], (size_t)B * c.act_elems[c.n_gtail] * 4, cudaMemcpyDeviceToDevice, st);
+  if (grad_out) {
+    if (int rc = run_backward(c, w, B, math, nullptr, grad_out, st)) return rc;
+  }
+  return check_launch("cgs_forward_logits_and_grad");
+}
+
+extern "C" int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y,
+                                 cgs_stream_t stream) {
+  if (int rc = require_sm100()) return rc;
+  if (!L || !x || !y) return set_error(CGS_ERR_INVALID, "null argument");
+  ConvGemmParams p;
+  if (int rc = make_forward_params(*L, B, x, y, p)) return rc;
+  return launch_gemm(p, L->w_fwd, L->rows_fwd, L->kcols_fwd, math, (cudaStream_t)stream);
+}
+
+extern "C" int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, const float* dy, float* dx,
+                                  const float* x_fwd, int prev_act, cgs_stream_t stream) {
+  if (int rc = require_sm100()) return rc;
+  if (!L || !dy || !dx) return set_error(CGS_ERR_INVALID, "null argument");
+  ConvGemmParams p;
+  if (int rc = make_backward_params(*L, B, dy, dx, p)) return rc;
+  if (x_fwd && prev_act != CGS_ACT_NONE) {
+    p.epi = EPI_BWD;
+    p.aux = x_fwd;
+    p.act = prev_act;
+  }
+  return launch_gemm(p, L->w_bwd, L->rows_bwd, L->kcols_bwd, math, (cudaStream_t)stream);
+}
+
+// Host-only: the K ordering of a layer's packed weight matrix, so the packer (cgs/pack.py) never has to
+// re-derive the class / tap enumeration.  For K index q: ky[q], kx[q] = filter tap (or -1 for zero padding),
+// ch[q] = reduced channel.  Returns the K length (multiple of 32), or a negative status.
+extern "C" int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* ky, int32_t* kx, int32_t* ch,
+                                int64_t capacity) {
+  if (!L) return set_error(CGS_ERR_INVALID, "null layer");
+  ConvGemmParams p;
+  int rc = backward ? make_backward_params(*L, 1, nullptr, nullptr, p) : make_forward_params(*L, 1, nullptr, nullptr, p);
+  if (rc) return rc;
+  int64_t total = 0;
+  for (int c = 0; c < p.nclasses; ++c) total += (int64_t)p.cls[c].nkb * 32;
+  if (!ky || !kx || !ch) return total;
+  if (capacity < total) return set_error(CGS_ERR_INVALID, "pack map capacity too small");
+  if (L->type == CGS_LAYER_FC) {
+    for (int64_t q = 0; q < total; ++q) { ky[q] = 0; kx[q] = 0; ch[q] = (int32_t)q; }
+    return total;
+  }
+  // recover (ky,kx) from (dy,dx): strided pass dy = ky - pad ; transposed pass dy = (py + pad - ky)/2
+  const bool strided = (p.S == 2);
+  const int size_for_pad = (L->type == CGS_LAYER_CONV) ? L->hin : L->hin * 2;
+  const int size_for_pad_x = (L->type == CGS_LAYER_CONV) ? L->win : L->win * 2;
+  const int pad_y = same_pad_before(size_for_pad, L->k), pad_x = same_pad_before(size_for_pad_x, L->k);
+  for (int c = 0; c < p.nclasses; ++c) {
+    const GemmClass& g = p.cls[c];
+    const int cin_k = p.cblocks ? p.cblocks * 32 : 4;
+    const int64_t klen = (int64_t)g.nkb * 32;
+    for (int64_t q = 0; q < klen; ++q) {
+      const int t = (int)(q / cin_k);
+      const int cc = (int)(q % cin_k);
+      const int64_t o = g.k0 + q;
+      if (t >= g.ntaps) { ky[o] = -1; kx[o] = -1; ch[o] = cc; continue; }
+      if (strided) {
+        ky[o] = g.dy[t] + pad_y;
+        kx[o] = g.dx[t] + pad_x;
+      } else {
+        ky[o] = g.oy0 + pad_y - 2 * g.dy[t];
+        kx[o] = g.ox0 + pad_x - 2 * g.dx[t];
+      }
+      ch[o] = cc;
+    }
+  }
+  return total;
+}
+
+// Host-only introspection (no GPU needed): the gathered-GEMM parameters a layer pass is lowered to, flattened to
+// int32 so tests can replay the exact gather on the CPU.  Layout: [IH, IW, Cs, cblocks, MH, MW, S, M, OH, OW, ON,
+// os, N, nclasses] then per class [k0, nkb, ntaps, oy0, ox0, dy[32], dx[32]].  Returns the number of ints.
+extern "C" int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
+                                         int64_t capacity) {
+  if (!L) return set_error(CGS_ERR_INVALID, "null layer");
+  ConvGemmParams p;
+  int rc = backward ? make_backward_params(*L, B, nullptr, nullptr, p) : make_forward_params(*L, B, nullptr, nullptr, p);
+  if (rc) return rc;
+  const int64_t need = 14 + (int64_t)p.nclasses * (5 + 2 * kMaxTaps);
+  if (!out) return need;
+  if (capacity < need) return set_error(CGS_ERR_INVALID, "capacity too small");
+  int32_t* o = out;
+  const int head[14] = {p.IH, p.IW, p.Cs, p.cblocks, p.MH, p.MW, p.S, p.M, p.OH, p.OW, p.ON, p.os, p.N, p.nclasses};
+  for (int i = 0; i < 14; ++i) *o++ = head[i];
+  for (int c = 0; c < p.nclasses; ++c) {
+    const GemmClass& g = p.cls[c];
+    *o++ = g.k0; *o++ = g.nkb; *o++ = g.ntaps; *o++ = g.oy0; *o++ = g.ox0;
+    for (int t = 0; t < kMaxTaps; ++t) *o++ = g.dy[t];
+    for (int t = 0; t < kMaxTaps; ++t) *o++ = g.dx[t];
+  }
+  return need;
+}

@@ -1,0 +1,156 @@
+"""Drop-in for the reference's ``sampling/collaborator.py`` (graph refiner of the image path).
+
+Same names as ``sampling/collaborator.py:7-88``: ``Refiner(rollout_steps, rollout_rate, rollout_method)``,
+``set_env(discriminator, feature_to_data, func_loss)``, ``set_constraints(vmin, vmax)``,
+``compute_forward_logits_and_grad(feature)``, ``build_refiner(fake_feature, real_batch, mode)`` and the result
+attributes ``default_logit / optimal_logit / optimal_step / optimal_feature / current_feature / current_logit``.
+
+Semantic shift: the reference builds a symbolic TF graph from python callables; here
+``discriminator`` / ``feature_to_data`` are network specs (``cgs.nets.discriminator_spec(spec)`` /
+``feature_to_data_spec(spec)``) and ``build_refiner`` runs eagerly and returns the refined batch.
+``func_loss`` must be the BCE-with-ones marker ``cgs.nets.loss_refine`` (nsgan/GAN.py:176-177).
+BatchNorm runs in inference mode (folded), see DESIGN.md for the delta to the reference's training-mode D.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+try:
+    from . import _paths  # noqa: F401
+    from .policy import PolicyAdaptive
+except ImportError:
+    import _paths  # noqa: F401
+    from policy import PolicyAdaptive
+from cgs import lib as L
+from cgs import nets as N
+from cgs import runtime as R
+
+
+class Refiner():
+    def __init__(self, rollout_steps, rollout_rate, rollout_method="momentum", math="tf32"):
+        self.forward_steps = rollout_steps
+        self.optimizer = PolicyAdaptive(rollout_rate, rollout_method)
+        self.log = False
+        self.vmin = None
+        self.vmax = None
+        self.math = math
+        self.early_exit_logit = None      # opt-in (README.md:13); None = reference behaviour (best of K)
+        self._ws = R.Workspace()
+        self.real_logits = None
+        self.real_logits_mean = None
+        self.forward_grad = None
+
+    def set_env(self, discriminator, feature_to_data, func_loss):
+        spec_d = discriminator.spec if isinstance(discriminator, N._Role) else discriminator
+        spec_g = feature_to_data.spec if isinstance(feature_to_data, N._Role) else feature_to_data
+        if not isinstance(spec_d, N.NetSpec) or not isinstance(spec_g, N.NetSpec):
+            raise TypeError("discriminator / feature_to_data must be cgs.nets specs (python callables cannot be fused)")
+        if not getattr(func_loss, "is_bce_with_ones", False):
+            raise NotImplementedError("only the reference's BCE-with-ones refinement loss is built (nsgan/GAN.py:176-177)")
+        self.discriminator = discriminator
+        self.feature_to_data = feature_to_data
+        self.func_loss = func_loss
+        self._d = spec_d.d
+        self._g = spec_g.gtail
+        self._spec = spec_g
+        self._cimg = spec_g.image_shape[2]
+
+    def set_constraints(self, vmin, vmax):
+        self.vmin = vmin
+        self.vmax = vmax
+        print("set_constraints: self.vmin = {:.2f}, self.vmax = {:.2f}".format(self.vmin, self.vmax))
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, B, dev):
+        nbytes = L.load().cgs_refine_workspace_bytes(C.byref(self._g.desc), C.byref(self._d.desc), B)
+        if nbytes == 0:
+            L.check(-1 if not L.last_error() else -2)
+        return self._ws.get(nbytes, dev)
+
+    def _img_shape(self, B):
+        h, w, c = self._spec.image_shape
+        return (B, h, w, N.cstride(c))
+
+    def compute_forward_logits_and_grad(self, current_feature):
+        """collaborator.py:26-39 -> (per-sample logit [B], d sum(loss) / d feature)."""
+        dev = self._spec.device
+        feat, _ = R.to_device(current_feature, torch.float32, dev)
+        B = feat.shape[0]
+        logit = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(feat)
+        ws = self._workspace(B, dev)
+        L.check(L.load().cgs_forward_logits_and_grad(C.byref(self._g.desc), C.byref(self._d.desc), L.MATH_IDS[self.math],
+                                                     B, L.ptr(feat), L.ptr(logit), L.ptr(grad), None, L.ptr(ws),
+                                                     ws.numel(), L.stream_ptr()))
+        return logit, grad
+
+    def feature_to_image(self, feature):
+        """feature_to_data(feature) (nsgan/GAN.py:94-101) -> [B,h,w,c] and its logit."""
+        dev = self._spec.device
+        feat, _ = R.to_device(feature, torch.float32, dev)
+        B = feat.shape[0]
+        logit = torch.empty(B, dtype=torch.float32, device=dev)
+        img = torch.empty(self._img_shape(B), dtype=torch.float32, device=dev)
+        ws = self._workspace(B, dev)
+        L.check(L.load().cgs_forward_logits_and_grad(C.byref(self._g.desc), C.byref(self._d.desc), L.MATH_IDS[self.math],
+                                                     B, L.ptr(feat), L.ptr(logit), None, L.ptr(img), L.ptr(ws),
+                                                     ws.numel(), L.stream_ptr()))
+        return img[..., :self._cimg], logit
+
+    def build_refiner(self, fake_feature, real_batch=None, mode='deterministic', prob_indices=None,
+                      keep_optimal_feature=False):
+        if mode not in ('deterministic', 'probabilistic'):
+            raise NotImplementedError(mode)
+        method = self.optimizer.method
+        if method == 'ladam':
+            # the reference calls apply_gradient without a loss here (collaborator.py:66) -> policy.py:51 fails
+            raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'float'")
+        if method not in ('sgd', 'momentum'):
+            raise NotImplementedError(method)                     # policy.py:64
+        dev = self._spec.device
+        lib = L.load()
+        feat_in, was_np = R.to_device(fake_feature, torch.float32, dev)
+        if tuple(feat_in.shape[1:]) != self._spec.feature_shape:
+            raise ValueError("feature shape %s does not match the spec %s" % (tuple(feat_in.shape[1:]), self._spec.feature_shape))
+        B = feat_in.shape[0]
+        feat = feat_in.clone()                                    # tf.identity (collaborator.py:48,58)
+        best_img = torch.empty(self._img_shape(B), dtype=torch.float32, device=dev)
+        best_logit = torch.empty(B, dtype=torch.float32, device=dev)
+        best_step = torch.empty(B, dtype=torch.float32, device=dev)
+        default_logit = torch.empty(B, dtype=torch.float32, device=dev)
+        best_feat = torch.empty_like(feat) if keep_optimal_feature else None
+        idx = None
+        if mode == 'probabilistic':
+            if prob_indices is None:
+                prob_indices = np.random.randint(self.forward_steps + 1, size=B)      # collaborator.py:56
+            idx, _ = R.to_device(np.asarray(prob_indices, dtype=np.int32), torch.int32, dev)
+        cfg = L.RefineCfg()
+        cfg.steps = int(self.forward_steps)
+        cfg.rate = float(self.optimizer.lambda_)
+        cfg.method = L.POLICY_IDS[method]
+        cfg.alpha = float(self.optimizer.alpha_)
+        cfg.mode = L.MODE_PROBABILISTIC if mode == 'probabilistic' else L.MODE_DETERMINISTIC
+        cfg.clip = 1 if (self.vmin and self.vmax) else 0           # collaborator.py:69 (truthiness, sic)
+        cfg.vmin = float(self.vmin) if cfg.clip else 0.0
+        cfg.vmax = float(self.vmax) if cfg.clip else 0.0
+        cfg.math = L.MATH_IDS[self.math]
+        cfg.early_exit = 0 if self.early_exit_logit is None else 1
+        cfg.exit_logit = float(self.early_exit_logit or 0.0)
+        ws = self._workspace(B, dev)
+        L.check(lib.cgs_refine_conv(C.byref(self._g.desc), C.byref(self._d.desc), C.byref(cfg), B, L.ptr(feat),
+                                    L.ptr(best_img), L.ptr(best_logit), L.ptr(best_step), L.ptr(default_logit),
+                                    L.ptr(idx), L.ptr(best_feat), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        self.optimizer.reset_moving_average()                       # collaborator.py:86
+        self.current_feature = feat
+        self.default_logit = default_logit
+        self.optimal_logit = best_logit
+        self.optimal_step = best_step
+        self.optimal_feature = best_feat
+        self.current_logit = None
+        refined = best_img[..., :self._cimg]                        # == feature_to_data(optimal_feature), :88
+        if was_np:
+            return refined.cpu().numpy()
+        return refined

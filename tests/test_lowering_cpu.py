@@ -1,0 +1,61 @@
+"""Host-side lowering + weight packing, checked on the CPU against the oracle's TF-semantics layers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as onets
+
+import emulate
+
+
+def _arches():
+    return ["mnist", "dcgan32_l1", "dcgan64_l3"]
+
+
+def test_arch_builders_agree(cgs_lib):
+    from cgs import nets as N
+    for name in _arches() + ["dcgan64_l1", "dcgan64_l4", "dcgan32_l2"]:
+        assert N.get_arch(name) == onets.get_arch(name)
+
+
+@pytest.mark.parametrize("arch_name", _arches())
+def test_layer_forward_and_dgrad_lowering(cgs_lib, arch_name):
+    from cgs import nets as N
+    arch = N.get_arch(arch_name)
+    w = onets.init_weights(arch, seed=7)
+    rng = np.random.RandomState(0)
+    B = 2
+    for scope, layers in (("generator", arch["gtail"]), ("discriminator", arch["d"])):
+        for layer in layers:
+            if layer["type"] == "fc" and layer["cout"] == 1:
+                continue
+            wf, bf = N.fold_layer(layer, scope, w)
+            w_fwd, w_bwd, bias = N.pack_layer(layer, wf, bf)
+            cin, cout = layer["cin"], layer["cout"]
+            if layer["type"] == "fc":
+                x = rng.standard_normal((B, cin)).astype(np.float32)
+            else:
+                x = rng.standard_normal((B, layer["hin"], layer["win"], cin)).astype(np.float32)
+            # oracle forward (pre-activation, BN inference) and its data-gradient
+            xt = torch.from_numpy(x).requires_grad_(True)
+            Lnoact = dict(layer, act="none")
+            y = onets.run_layers(xt, [Lnoact], scope, w, "inference")
+            dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
+            (dx,) = torch.autograd.grad((y * dy).sum(), xt)
+            # replay forward
+            pf = emulate.gemm_params(layer, False, B)
+            cs_in = pf["Cs"]
+            xp = np.zeros((B, pf["IH"], pf["IW"], cs_in))
+            xp[..., :cin] = x.reshape(B, pf["IH"], pf["IW"], cin)
+            acc = emulate.replay(pf, xp, w_fwd.numpy(), B)
+            got = acc[..., :cout] + bias.numpy()[:cout]
+            ref = y.detach().numpy().reshape(got.shape)
+            assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), (layer["name"], "fwd")
+            assert np.all(acc[..., cout:] == 0)
+            # replay backward
+            pb = emulate.gemm_params(layer, True, B)
+            dyp = np.zeros((B, pb["IH"], pb["IW"], pb["Cs"]))
+            dyp[..., :cout] = dy.numpy().reshape(B, pb["IH"], pb["IW"], cout)
+            gacc = emulate.replay(pb, dyp, w_bwd.numpy(), B)
+            gref = dx.numpy().reshape(B, pb["OH"], pb["OW"], cin)
+            assert np.abs(gacc[..., :cin] - gref).max() <= 1e-4 * max(1.0, np.abs(gref).max()), (layer["name"], "bwd")
