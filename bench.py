@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- refined samples / second of the collaborative-sampling hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic proposals: K_refine refinement steps through
+G-tail + D (sampling/collaborator.py:41-88) followed by the MH-GAN accept-reject pass (sampling/idpsampler.py)
+on the refined batch.  Default workload = BASELINE.json configs[1]: infoGAN-MNIST nets, refine at the [7,7,128]
+map, batch 1024 per GPU, K_refine = 50, momentum, rate 0.1.  With N > 1 (torchrun) every rank refines its own
+shard (weak scaling); NCCL only gathers scores / accepted rows / statistics.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
+public drop-in API with pinned HOST inputs and host outputs; `roofline` is for the dominant kernel
+(conv_gemm_tc_kernel, tcgen05 TF32); `cpu_baseline` is the CPU oracle port of the same path timed on this box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "collaborative-gan-sampling_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "refined_samples_per_sec"
+UNIT = "samples/s"
+
+WORKLOADS = {
+    # name: (arch, batch per GPU, refine steps, method, rate, weight gain)
+    "mnist": ("mnist", 1024, 50, "momentum", 0.1, 3.0),
+    "dcgan32_l1": ("dcgan32_l1", 1024, 50, "momentum", 0.1, 2.5),
+    "dcgan64_l1": ("dcgan64_l1", 1024, 50, "momentum", 0.1, 2.5),
+    "dcgan64_l2": ("dcgan64_l2", 1024, 50, "momentum", 0.1, 2.5),
+    "dcgan64_l3": ("dcgan64_l3", 1024, 50, "momentum", 0.1, 2.5),
+    "dcgan64_l4": ("dcgan64_l4", 1024, 50, "momentum", 0.1, 2.5),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override batch per GPU")
+    ap.add_argument("--refine-steps", type=int, default=0, help="override K_refine")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        # median over the upper half = clocks under load (idle samples before/after the region are low)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline / --impl reference)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_port_step(arch_name, gain, batch, refine_steps, method, rate, seed=0):
+    """One hot-path pass on the host: oracle graph refiner (FP32 torch-CPU restatement of
+    sampling/collaborator.py over the nsgan nets, D BN in inference mode) + oracle MH chain.  Returns seconds."""
+    import numpy as np
+    import torch
+    from oracle import graph_refiner as gr
+    from oracle import nets as onets
+    from oracle import sampling_np as snp
+    arch = onets.get_arch(arch_name)
+    w = onets.scale_weights_for_signal(arch, onets.init_weights(arch, seed=2019), gain)
+    w = {k: torch.from_numpy(v) for k, v in w.items()}
+    rng = np.random.RandomState(seed)
+    h0 = torch.from_numpy(np.maximum(rng.standard_normal((batch,) + tuple(arch["feature_shape"])), 0).astype(np.float32))
+    t0 = time.perf_counter()
+    out = gr.build_refiner(h0, arch, w, refine_steps, rate, method=method)
+    sig = torch.sigmoid(out["optimal_logit"]).numpy().reshape(-1, 1)
+    emit, _, _, _ = snp.mh_chain(sig, rng.rand(batch), np.float32(0.5), 1, 20, 0)
+    _ = out["refined"].numpy()[emit] if len(emit) else None
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    import torch
+    arch_name, batch, ksteps, method, rate, gain = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 64        # the reference's default batch (nsgan/main.py:32); bounded so the run ends in minutes
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_port_step(arch_name, gain, sample_b, ksteps, method, rate)
+    times = [cpu_port_step(arch_name, gain, sample_b, ksteps, method, rate, seed=i) for i in range(args.steps)]
+    total = sum(times)
+    value = sample_b * args.steps / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: refine K=%d %s rate %.2g + MH(T=20)" % (arch_name, ksteps, method, rate),
+                   "batch_per_step": sample_b, "note": "CPU oracle port of the reference path (TF 1.13 is not installable); "
+                   "each step is a bounded %d-row sample of the %d-row workload" % (sample_b, batch)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d rows, K=%d" % (args.steps, sample_b, ksteps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ours
+# ----------------------------------------------------------------------------------------------------------
+def measure_tf32_peak(torch, dev):
+    """cuBLAS TF32 GEMM 8192^3, best of 5 (burst) -- the tensor roofline denominator for kind::tf32."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            a @ b
+            e.record()
+            e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def roofline_profile(torch, spec, arch, batch, math, dev, reps=3):
+    """Time every GEMM launch of one refinement step (forward chain + data-gradient chain) with CUDA events on the
+    launching stream, at the benchmark batch size.  Returns (flops per step, seconds per step, per-layer rows)."""
+    import ctypes as C
+    from cgs import lib as L
+    from cgs import nets as N
+    from cgs import synthetic as S
+    lib = L.load()
+    chain = [(l, spec.gtail.layer_desc(i)) for i, l in enumerate(arch["gtail"])] + \
+            [(l, spec.d.layer_desc(i)) for i, l in enumerate(arch["d"][:-1])]
+    rows, tot_f, tot_t = [], 0.0, 0.0
+    for layer, desc in chain:
+        cin, cout = layer["cin"], layer["cout"]
+        if layer["type"] == "fc":
+            xs, ys = (batch, cin), (batch, N.cstride(cout))
+        elif layer["type"] == "conv":
+            xs = (batch, layer["hin"], layer["win"], N.cstride(cin))
+            ys = (batch, (layer["hin"] + 1) // 2, (layer["win"] + 1) // 2, N.cstride(cout))
+        else:
+            xs = (batch, layer["hin"], layer["win"], N.cstride(cin))
+            ys = (batch, layer["hin"] * 2, layer["win"] * 2, N.cstride(cout))
+        x = torch.randn(xs, device=dev)
+        y = torch.empty(ys, device=dev)
+        dy = torch.randn(ys, device=dev)
+        dx = torch.empty(xs, device=dev)
+        flops = 2.0 * S.layer_macs(layer) * batch
+        for name, fn in (("fwd", lambda: lib.cgs_layer_forward(C.byref(desc), L.MATH_IDS[math], batch, L.ptr(x), L.ptr(y), L.stream_ptr())),
+                         ("bwd", lambda: lib.cgs_layer_backward(C.byref(desc), L.MATH_IDS[math], batch, L.ptr(dy), L.ptr(dx), L.ptr(x), 1, L.stream_ptr()))):
+            L.check(fn())
+            best = 1e9
+            for _ in range(reps):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                L.check(fn())
+                e.record()
+                e.synchronize()
+                best = min(best, s.elapsed_time(e) * 1e-3)
+            rows.append({"layer": layer["name"] + "." + name, "us": round(best * 1e6, 1), "tflops": round(flops / best / 1e12, 1)})
+            tot_f += flops
+            tot_t += best
+    return tot_f, tot_t, rows
+
+
+def run_ours(args, wl):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cgs import dist as D
+    from cgs import lib as L
+    from cgs import nets as N
+    from cgs import synthetic as S
+    from sampling.collaborator import Refiner
+    from sampling.idpsampler import IndependenceSampler
+
+    arch_name, batch, ksteps, method, rate, gain = wl
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: libcgs has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    arch = N.get_arch(arch_name)
+    weights = S.init_weights(arch, seed=2019, gain=gain)
+    spec = N.NetSpec(arch, weights, dev)
+    refiner = Refiner(ksteps, rate, method, math=args.math)
+    refiner.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    mh = IndependenceSampler(T=20, rng="philox", seed=2019)          # nsgan/GAN.py:169
+    mh.set_score_curr(np.float32(0.5))
+    lo, hi = rank * batch, (rank + 1) * batch
+    h0_host = torch.from_numpy(S.proposal_features(arch, batch, seed=1000 + rank)).pin_memory()
+    h0_dev = h0_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def hot_path(h0):
+        """refine -> global scores -> MH chain -> accepted rows (global order)."""
+        x = refiner.build_refiner(h0, None, "deterministic")
+        sig_local = torch.sigmoid(refiner.optimal_logit)
+        sig = D.gather_scores(sig_local) if world > 1 else sig_local
+        emit = mh.select(sig)
+        if world > 1:
+            acc = D.gather_accepted(x, emit.long(), lo, hi)
+        else:
+            acc = mh.gather(x)                                   # cgs_gather_rows on the emitted source rows
+        return x, acc, sig_local
+
+    # ---- device-timed region: inputs resident in HBM ------------------------------------------------------
+    for _ in range(args.warmup):
+        hot_path(h0_dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.cgs_launch_count()
+    step_ms = []
+    n_acc = 0
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        flush.fill_(1)                       # flush L2 between timed iterations (outside the event pair)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        x, acc, sig_local = hot_path(h0_dev)
+        e.record()
+        e.synchronize()
+        step_ms.append(s.elapsed_time(e))
+        n_acc = acc.shape[0]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = (lib.cgs_launch_count() - launches0) // max(args.steps, 1)
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = world * batch * args.steps / total_s
+
+    # ---- end-to-end through the public API: pinned host inputs, host outputs ------------------------------
+    out_host = torch.empty((batch,) + tuple(arch["image_shape"]), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    hot_path(h0_host)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        x, acc, sig_local = hot_path(h0_host)                   # H2D of the proposals happens inside build_refiner
+        out_host.copy_(x, non_blocking=True)                     # D2H of the refined batch
+        acc_host = acc.cpu()                                     # D2H of the accepted samples
+        stats = D.reduce_stats(acc.shape[0], sig_local.sum(), sig_local.max()) if world > 1 else \
+            (float(acc.shape[0]), float(sig_local.sum()), float(sig_local.max()))
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * e2e_steps / float(e2e_t.item())
+    h2d = h0_host.numel() * 4
+    d2h = out_host.numel() * 4 + acc_host.numel() * 4 + 3 * 8
+
+    line = None
+    if rank == 0:
+        flops_sample = S.refine_flops_per_sample(arch, ksteps)
+        roof = None
+        if not args.no_roofline:
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            bf16_peak, src = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16)"
+            if os.path.exists(peaks_path):
+                with open(peaks_path) as f:
+                    bf16_peak = float(json.load(f)["bf16_tflops"])
+                src = "MEASURED_PEAKS.json bf16_tflops (burst)"
+            tf32_cublas = measure_tf32_peak(torch, dev)
+            f_step, t_step, rows = roofline_profile(torch, spec, arch, batch, args.math, dev)
+            achieved = f_step / t_step / 1e12
+            peak = 0.5 * bf16_peak
+            roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 kind::tf32, all layer passes of one step)",
+                    "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
+                    "frac": round(achieved / peak, 4), "traffic": None,
+                    "peak_source": "0.5 x %s (TF32 = half the BF16 rate)" % src,
+                    "cublas_tf32_tflops_same_run": round(tf32_cublas, 1),
+                    "frac_of_cublas_tf32": round(achieved / tf32_cublas, 4),
+                    "algorithmic_gflop_per_launch_set": round(f_step / 1e9, 2),
+                    "step_share_of_gemm_time": round(t_step * (2 * ksteps + 1) / 2.0 / (total_s / args.steps), 3),
+                    "per_layer": rows}
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample_b = 64
+            t = min(cpu_port_step(arch_name, gain, sample_b, ksteps, method, rate, seed=i) for i in range(2))
+            cpu = {"value": sample_b / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "%d rows x K=%d (+MH), best of 2, torch-CPU FP32 oracle port" % (sample_b, ksteps)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "%s: refine K=%d %s rate %.2g + MH(T=20), batch %d/GPU" % (arch_name, ksteps, method, rate, batch),
+                       "global_batch": world * batch, "parallelism": "dp%d (sharded batch, no collective in the K loop)" % world,
+                       "l2": "flushed (256 MiB write) between timed iterations; per-step working set also exceeds L2",
+                       "weights": "random init seed 2019, gain %.1f" % gain,
+                       "gflop_per_sample": round(flops_sample / 1e9, 3)},
+            "tflops_algorithmic": round(world * batch * flops_sample / (total_s / args.steps) / 1e12, 2),
+            "accepted_per_step": int(n_acc),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches * args.steps),
+            "gpu_launches_per_step": int(launches),
+            "clocks": clk,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    args = parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.batch:
+        wl[1] = args.batch
+    if args.refine_steps:
+        wl[2] = args.refine_steps
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

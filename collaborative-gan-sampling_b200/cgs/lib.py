@@ -66,6 +66,7 @@ class CgsError(RuntimeError):
 _SIGNATURES = {
     "cgs_version": (C.c_int, []),
     "cgs_last_error": (C.c_char_p, []),
+    "cgs_launch_count": (C.c_longlong, []),
     "cgs_policy_step": (C.c_int, [C.POINTER(PolicyCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     "cgs_drs_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -1,12 +1,18 @@
 // Library-level entry points: version, thread-local error string, device gate.
 #include "common.h"
 
+#include <atomic>
+
 namespace cgs {
 
 char* error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
 
 int require_sm100() {
   static thread_local int cached_dev = -1;
@@ -26,5 +32,7 @@ int require_sm100() {
 
 }  // namespace cgs
 
+namespace cgs { long long launches_total(); }
+extern "C" long long cgs_launch_count(void) { return cgs::launches_total(); }
 extern "C" int cgs_version(void) { return CGS_ABI_VERSION; }
 extern "C" const char* cgs_last_error(void) { return cgs::error_buffer(); }

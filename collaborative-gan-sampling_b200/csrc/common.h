@@ -27,4 +27,7 @@ inline int check_launch(const char* what) {
 // The product never runs on anything but sm_100: refuse loudly instead of falling back.
 int require_sm100();
 
+// Process-wide count of kernels launched by the library (cgs_launch_count).
+void count_launch(int n = 1);
+
 }  // namespace cgs

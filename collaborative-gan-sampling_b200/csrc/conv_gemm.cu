@@ -371,7 +371,7 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   }
   const int total = p.m_tiles * p.n_tiles * p.nclasses;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap);
+  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
@@ -410,7 +410,7 @@ int launch_conv_gemm_simt(const ConvGemmParams& p, const float* w, int w_rows, i
   const long long total = (long long)p.nclasses * p.M * (p.ON / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  conv_gemm_simt_kernel<<<(int)blocks, 256, 0, stream>>>(p, w, w_cols);
+  conv_gemm_simt_kernel<<<(int)blocks, 256, 0, stream>>>(p, w, w_cols); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_simt launch: %s", cudaGetErrorString(e));
   return CGS_OK;

@@ -268,7 +268,7 @@ extern "C" int cgs_mlp2d_score(const cgs_mlp_desc* d, const float* x, int64_t n,
   cudaError_t e = cudaFuncSetAttribute(mlp2d_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   mlp2d_score_kernel<<<s.grid, s.threads, s.smem, (cudaStream_t)stream>>>(*d, x, n, 1.0f / (float)n_mean, sigmoid_out,
-                                                                         logit_out, saliency_out);
+                                                                         logit_out, saliency_out); count_launch();
   return check_launch("cgs_mlp2d_score");
 }
 
@@ -291,6 +291,6 @@ extern "C" int cgs_refine_mlp2d(const cgs_mlp_desc* d, const cgs_refine2d_cfg* c
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   mlp2d_refine_kernel<<<s.grid, s.threads, s.smem, (cudaStream_t)stream>>>(
       *d, make_policy_consts(cfg->policy), cfg->steps, 1.0f / (float)n_mean, cfg->real_sigmoid_mean, x_in, n, best_x,
-      best_loss, best_step, traj_out);
+      best_loss, best_step, traj_out); count_launch();
   return check_launch("cgs_refine_mlp2d");
 }

@@ -444,7 +444,7 @@ static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams
   hp.feature = w.act[0];
   hp.feat_elems = (int)c.act_elems[0];
   hp.cur_logit = w.cur_logit;
-  head_kernel<<<(unsigned)B, 256, 0, st>>>(hp);
+  head_kernel<<<(unsigned)B, 256, 0, st>>>(hp); count_launch();
   return check_launch("head_kernel");
 }
 

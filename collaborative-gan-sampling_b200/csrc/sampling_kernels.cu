@@ -280,9 +280,9 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ flags, int64_
 
 int compact_flags(const uint8_t* flags, int64_t n, int* block_counts, int* idx_out, int* count_out, cudaStream_t st) {
   const int nb = (int)((n + kChunk - 1) / kChunk);
-  compact_count_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts);
-  compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nb, count_out);
-  compact_scatter_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts, idx_out);
+  compact_count_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts); count_launch();
+  compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nb, count_out); count_launch();
+  compact_scatter_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts, idx_out); count_launch();
   return check_launch("compact_flags");
 }
 
@@ -498,10 +498,11 @@ extern "C" int cgs_policy_step(const cgs_policy_cfg* cfg, float* theta, const fl
   if (rows == 0) return CGS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const PolicyConsts c = make_policy_consts(*cfg);
-  if (cfg->method == CGS_POLICY_LADAM)
-    policy_loss_avg_kernel<<<grid_for(rows), kBlock, 0, st>>>(c, loss, loss_avg, first, rows);
+  if (cfg->method == CGS_POLICY_LADAM) {
+    policy_loss_avg_kernel<<<grid_for(rows), kBlock, 0, st>>>(c, loss, loss_avg, first, rows); count_launch();
+  }
   policy_step_kernel<<<grid_for(rows * cols), kBlock, 0, st>>>(c, theta, grad, momentum, mean_square, loss_avg, first,
-                                                               rows, cols, cols > 2 ? 1 : 0);
+                                                               rows, cols, cols > 2 ? 1 : 0); count_launch();
   return check_launch("cgs_policy_step");
 }
 
@@ -515,7 +516,7 @@ extern "C" size_t cgs_drs_workspace_bytes(int64_t n) {
 extern "C" int cgs_drs_set_score_max(const void* score_max, int dtype, double* d_tilde_m, cgs_stream_t stream) {
   if (int rc = require_sm100()) return rc;
   if (!score_max || !d_tilde_m) return set_error(CGS_ERR_INVALID, "null argument");
-  drs_score_max_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(score_max, dtype, d_tilde_m);
+  drs_score_max_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(score_max, dtype, d_tilde_m); count_launch();
   return check_launch("cgs_drs_set_score_max");
 }
 
@@ -543,13 +544,13 @@ extern "C" int cgs_drs_accept(const void* sigmoids, int sig_dtype, int64_t n, co
   unsigned int* hist = (unsigned int*)base;  base += al(1024);
   int* bcounts = (int*)base;
   const int grid = grid_for(n);
-  drs_logit_kernel<<<grid, kBlock, 0, st>>>(sigmoids, sig_dtype, n, f, bmax);
-  drs_update_max_kernel<<<1, kBlock, 0, st>>>(bmax, grid, d_tilde_m);
-  drs_f_kernel<<<grid, kBlock, 0, st>>>(f, n, d_tilde_m, epsilon, bmax);
+  drs_logit_kernel<<<grid, kBlock, 0, st>>>(sigmoids, sig_dtype, n, f, bmax); count_launch();
+  drs_update_max_kernel<<<1, kBlock, 0, st>>>(bmax, grid, d_tilde_m); count_launch();
+  drs_f_kernel<<<grid, kBlock, 0, st>>>(f, n, d_tilde_m, epsilon, bmax); count_launch();
   if (shift_percent < 0.0) {
-    set_double_kernel<<<1, 1, 0, st>>>(gamma, 0.0);                       // shift_percent=None: no shift
+    set_double_kernel<<<1, 1, 0, st>>>(gamma, 0.0); count_launch();                       // shift_percent=None: no shift
   } else if (shift_percent == 100.0) {
-    reduce_max_kernel<<<1, kBlock, 0, st>>>(bmax, grid, gamma);           // numpy percentile(.,100) == max
+    reduce_max_kernel<<<1, kBlock, 0, st>>>(bmax, grid, gamma); count_launch();           // numpy percentile(.,100) == max
   } else {
     // numpy 'linear': virtual index (n-1)*q/100 -> floor / ceil order statistics, lerp
     const double q = shift_percent / 100.0;
@@ -560,15 +561,15 @@ extern "C" int cgs_drs_accept(const void* sigmoids, int sig_dtype, int64_t n, co
     int64_t hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
     for (int which = 0; which < 2; ++which) {
       unsigned long long* s = sel + 2 * which;
-      select_init_kernel<<<1, 256, 0, st>>>(s, (unsigned long long)(which ? hi : lo), hist);
+      select_init_kernel<<<1, 256, 0, st>>>(s, (unsigned long long)(which ? hi : lo), hist); count_launch();
       for (int pass = 0; pass < 8; ++pass) {
-        select_hist_kernel<<<grid, kBlock, 0, st>>>(f, n, s, pass, hist);
-        select_pick_kernel<<<1, 256, 0, st>>>(s, pass, hist);
+        select_hist_kernel<<<grid, kBlock, 0, st>>>(f, n, s, pass, hist); count_launch();
+        select_pick_kernel<<<1, 256, 0, st>>>(s, pass, hist); count_launch();
       }
     }
-    percentile_lerp_kernel<<<1, 1, 0, st>>>(sel, sel + 2, t, gamma);
+    percentile_lerp_kernel<<<1, 1, 0, st>>>(sel, sel + 2, t, gamma); count_launch();
   }
-  drs_accept_kernel<<<grid, kBlock, 0, st>>>(f, n, gamma, uniforms, philox_seed, philox_offset, accept_out, prob_out);
+  drs_accept_kernel<<<grid, kBlock, 0, st>>>(f, n, gamma, uniforms, philox_seed, philox_offset, accept_out, prob_out); count_launch();
   if (int rc = check_launch("cgs_drs_accept")) return rc;
   return compact_flags(accept_out, n, bcounts, idx_out, count_out, st);
 }
@@ -609,16 +610,16 @@ extern "C" int cgs_mh_accept(const void* sigmoids, int sig_dtype, int64_t n, con
   int* plan = (int*)base;      base += al(8);
   int* bcounts = (int*)base;
   mh_next_kernel<<<grid_for(n + 1, 128, 148 * 16), 128, 0, st>>>(sigmoids, sig_dtype, n, uniforms, philox_seed,
-                                                                 philox_offset, d_curr, d_kind, next);
-  mh_exit_kernel<<<nseg, kBlock, 0, st>>>(next, n, exitn);
-  mh_entries_kernel<<<1, 256, 0, st>>>(next, exitn, n, entry, nseg);
-  mh_mark_kernel<<<nseg, kBlock, 0, st>>>(next, n, entry, accepted_out);
+                                                                 philox_offset, d_curr, d_kind, next); count_launch();
+  mh_exit_kernel<<<nseg, kBlock, 0, st>>>(next, n, exitn); count_launch();
+  mh_entries_kernel<<<1, 256, 0, st>>>(next, exitn, n, entry, nseg); count_launch();
+  mh_mark_kernel<<<nseg, kBlock, 0, st>>>(next, n, entry, accepted_out); count_launch();
   if (int rc = check_launch("cgs_mh_accept")) return rc;
   if (int rc = compact_flags(accepted_out, n, bcounts, acc_idx, n_acc, st)) return rc;
   mh_plan_kernel<<<1, 1, 0, st>>>(sigmoids, sig_dtype, n, acc_idx, n_acc, thin_period, burn_in, d_curr, d_kind,
-                                  cnt_chain, plan, count_out);
+                                  cnt_chain, plan, count_out); count_launch();
   const int64_t max_emit = n / (thin_period + 1) + 1;
-  mh_emit_kernel<<<grid_for(max_emit), kBlock, 0, st>>>(acc_idx, n_acc, plan, thin_period, emit_src_out);
+  mh_emit_kernel<<<grid_for(max_emit), kBlock, 0, st>>>(acc_idx, n_acc, plan, thin_period, emit_src_out); count_launch();
   return check_launch("cgs_mh_accept");
 }
 
@@ -630,6 +631,6 @@ extern "C" int cgs_gather_rows(const void* src, int64_t row_bytes, const int32_t
   if (!src || !idx || !count || !dst) return set_error(CGS_ERR_INVALID, "null argument");
   int grid = (int)(max_rows < 148 * 16 ? max_rows : 148 * 16);
   gather_rows_kernel<<<grid, row_bytes >= 4096 ? 256 : 64, 0, (cudaStream_t)stream>>>(
-      (const uint8_t*)src, row_bytes, idx, count, max_rows, (uint8_t*)dst);
+      (const uint8_t*)src, row_bytes, idx, count, max_rows, (uint8_t*)dst); count_launch();
   return check_launch("cgs_gather_rows");
 }

@@ -96,12 +96,11 @@ class IndependenceSampler():
                            torch.tensor([self._cnt_host], dtype=torch.int32, device=dev))
         return self._state
 
-    def sampling(self, samples, sigmoids, uniforms=None):
+    def select(self, sigmoids, uniforms=None):
+        """Run the chain over the scores only; returns the emitted source rows (device int32, ascending)."""
         dev = R.require_cuda()
         lib = L.load()
         sig, _ = R.to_device(sigmoids)
-        smp, smp_np = R.to_device(samples)
-        assert smp.shape[0] == sig.shape[0]                     # idpsampler.py:21
         if sig.dtype not in (torch.float32, torch.float64):
             sig = sig.to(torch.float64)
         sig = sig.reshape(sig.shape[0], -1)[:, 0].contiguous()
@@ -134,6 +133,32 @@ class IndependenceSampler():
                                   L.ptr(count), L.ptr(ws), ws.numel(), L.stream_ptr()))
         k = int(count.item())
         self.last_accepted, self.last_emit_src = accepted[:n], emit[:k]
+        self._last_count = count
+        return self.last_emit_src
+
+    def gather(self, samples):
+        """Rows of ``samples`` emitted by the last ``select`` call, float32, in emission order."""
+        dev = R.require_cuda()
+        smp, smp_np = R.to_device(samples)
+        emit, count = self.last_emit_src, self._last_count
+        k = emit.numel()
+        if k == 0:
+            return R.back(torch.empty((0,), dtype=torch.float32, device=dev), smp_np)
+        src = (smp if smp.dtype == torch.float32 else smp.to(torch.float32)).contiguous()
+        out = torch.empty((k,) + tuple(src.shape[1:]), dtype=torch.float32, device=dev)
+        L.check(L.load().cgs_gather_rows(L.ptr(src), src[0].numel() * 4, L.ptr(emit), L.ptr(count), k, L.ptr(out),
+                                         L.stream_ptr()))
+        return R.back(out, smp_np)
+
+    def sampling(self, samples, sigmoids, uniforms=None):
+        dev = R.require_cuda()
+        lib = L.load()
+        smp, smp_np = R.to_device(samples)
+        nsig = sigmoids.shape[0]
+        assert smp.shape[0] == nsig                              # idpsampler.py:21
+        emit = self.select(sigmoids, uniforms)
+        k = emit.numel()
+        count = self._last_count
         if k == 0:
             out = torch.empty((0,), dtype=torch.float32, device=dev)        # np.asarray([], float32): shape (0,)
             return R.back(out, smp_np)

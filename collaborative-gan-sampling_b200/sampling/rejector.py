@@ -55,9 +55,8 @@ class Rejector(object):
         m = self._state(dev)
         L.check(L.load().cgs_drs_set_score_max(L.ptr(s), R.score_dtype(s), L.ptr(m), L.stream_ptr()))
 
-    def sampling(self, samples, sigmoids, epsilon=1e-8, shift_percent=60.0, ranking=None, uniforms=None):
-        if ranking is not None:
-            raise NotImplementedError        # rejector.py:35-36
+    def select(self, sigmoids, epsilon=1e-8, shift_percent=60.0, uniforms=None):
+        """Accept / reject on the scores only; returns the accepted rows (device int32, ascending)."""
         dev = R.require_cuda()
         lib = L.load()
         sig, _ = R.to_device(sigmoids)
@@ -65,9 +64,6 @@ class Rejector(object):
             sig = sig.to(torch.float64)
         sig = sig.reshape(-1)
         n = sig.numel()
-        smp, smp_np = R.to_device(samples)
-        if smp.shape[0] != n:
-            raise IndexError("boolean index did not match indexed array along dimension 0")
         u = None
         seed, offset = 0, 0
         if uniforms is not None:
@@ -90,6 +86,21 @@ class Rejector(object):
                                    L.stream_ptr()))
         k = int(count.item())                 # the one sync: the output is sized by the count
         self.last_accept, self.last_indices = accept, idx[:k]
+        self._last_count = count
+        return self.last_indices
+
+    def sampling(self, samples, sigmoids, epsilon=1e-8, shift_percent=60.0, ranking=None, uniforms=None):
+        if ranking is not None:
+            raise NotImplementedError        # rejector.py:35-36
+        dev = R.require_cuda()
+        lib = L.load()
+        smp, smp_np = R.to_device(samples)
+        nsig = sigmoids.shape[0] if hasattr(sigmoids, 'shape') else len(sigmoids)
+        if smp.shape[0] != nsig:
+            raise IndexError("boolean index did not match indexed array along dimension 0")
+        idx = self.select(sigmoids, epsilon, shift_percent, uniforms)
+        k = idx.numel()
+        count = self._last_count
         out = torch.empty((k,) + tuple(smp.shape[1:]), dtype=smp.dtype, device=dev)
         if k:
             row_bytes = smp[0].numel() * smp.element_size()

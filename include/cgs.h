@@ -44,6 +44,8 @@ enum cgs_status {
 #define CGS_ABI_VERSION 1
 CGS_API int cgs_version(void);
 CGS_API const char* cgs_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+CGS_API long long cgs_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Update policy.  Replaces sampling/policy.py:26-64 (PolicyAdaptive.apply_gradient), all three methods.

@@ -1,0 +1,159 @@
+"""GPU parity for the image path: per-layer forward / data-gradient and the K-step refinement vs the FP32 oracle.
+
+Tolerances: FP32 SIMT mode is compared at 2e-5 relative (summation order only); the TF32
+tensor-core mode at rel-L2 <= 1e-3 per layer pass (10-bit mantissa operands, FP32 accumulation).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_refiner as gr
+from oracle import nets as onets
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tf32": 1e-3}
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def pad_c(x, cs):
+    out = np.zeros(x.shape[:-1] + (cs,), np.float32)
+    out[..., :x.shape[-1]] = x
+    return out
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("dcgan32_l1", 3), ("dcgan64_l2", 2)])
+def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
+    from cgs import lib as L
+    from cgs import nets as N
+    arch = N.get_arch(arch_name)
+    w = onets.init_weights(arch, seed=11)
+    spec = N.NetSpec(arch, w, cuda_device)
+    rng = np.random.RandomState(1)
+    chain = [("generator", l, spec.gtail.layer_desc(i)) for i, l in enumerate(arch["gtail"])] + \
+            [("discriminator", l, spec.d.layer_desc(i)) for i, l in enumerate(arch["d"][:-1])]
+    worst = {}
+    for scope, layer, desc in chain:
+        cin, cout = layer["cin"], layer["cout"]
+        shp = (B, cin) if layer["type"] == "fc" else (B, layer["hin"], layer["win"], cin)
+        x = rng.standard_normal(shp).astype(np.float32)
+        xt = torch.from_numpy(x).requires_grad_(True)
+        y = onets.run_layers(xt, [layer], scope, w, "inference")
+        dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        # gradient w.r.t. the layer's PRE-activation output is what the backward GEMM consumes
+        ypre = onets.run_layers(xt, [dict(layer, act="none")], scope, w, "inference")
+        (dx,) = torch.autograd.grad((ypre * torch.from_numpy(dy)).sum(), xt)
+        cs_in, cs_out = N.cstride(cin), N.cstride(cout)
+        x_dev = torch.from_numpy(pad_c(x, cs_in)).to(cuda_device)
+        y_dev = torch.full(tuple(y.shape[:-1]) + (cs_out,), float("nan"), device=cuda_device)
+        L.check(cgs_lib.cgs_layer_forward(C.byref(desc), L.MATH_IDS[math], B, L.ptr(x_dev), L.ptr(y_dev), L.stream_ptr()))
+        torch.cuda.synchronize()
+        got = y_dev.cpu().numpy()
+        e = rel_l2(got[..., :cout], y.detach().numpy())
+        worst[layer["name"] + ".fwd"] = e
+        assert e <= TOL[math], (layer["name"], "fwd", e)
+        assert np.all(got[..., cout:] == 0), "padding channels must stay zero"
+        dy_dev = torch.from_numpy(pad_c(dy, cs_out)).to(cuda_device)
+        dx_dev = torch.full(tuple(x.shape[:-1]) + (cs_in,), float("nan"), device=cuda_device)
+        L.check(cgs_lib.cgs_layer_backward(C.byref(desc), L.MATH_IDS[math], B, L.ptr(dy_dev), L.ptr(dx_dev), None, 0,
+                                           L.stream_ptr()))
+        torch.cuda.synchronize()
+        gotg = dx_dev.cpu().numpy()
+        e = rel_l2(gotg[..., :cin], dx.numpy())
+        worst[layer["name"] + ".bwd"] = e
+        assert e <= TOL[math], (layer["name"], "bwd", e)
+    print(arch_name, math, {k: "%.2e" % v for k, v in worst.items()})
+
+
+def _make(arch_name, seed, gain, cuda_device):
+    from cgs import nets as N
+    arch = N.get_arch(arch_name)
+    w = onets.scale_weights_for_signal(arch, onets.init_weights(arch, seed=seed), gain)
+    return arch, w, N.NetSpec(arch, w, cuda_device)
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("arch_name,B,gain", [("mnist", 6, 3.0), ("dcgan32_l1", 4, 2.5), ("dcgan64_l3", 3, 2.5)])
+def test_forward_logits_and_grad(cgs_lib, cuda_device, arch_name, B, gain, math):
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 5, gain, cuda_device)
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(1)))
+    logit_ref, grad_ref, img_ref = gr.forward_logits_and_grad(h0, arch, w)
+    ref = Refiner(1, 0.1, math=math)
+    ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    logit, grad = ref.compute_forward_logits_and_grad(h0.to(cuda_device))
+    img, logit2 = ref.feature_to_image(h0.to(cuda_device))
+    tol = 5e-5 if math == "fp32" else 3e-3
+    gtol = tol if math == "fp32" else 8e-2     # TF32: ReLU masks of near-zero units flip -> gradient rel-L2 ~ sqrt(flip rate)
+    ltol = tol if math == "fp32" else 1.5e-2
+    print(arch_name, math, "logit", logit_ref.numpy(), "err", np.abs(logit.cpu().numpy() - logit_ref.numpy()).max(),
+          "grad rel", rel_l2(grad.cpu().numpy(), grad_ref.numpy()), "img rel", rel_l2(img.cpu().numpy(), img_ref.numpy()))
+    assert rel_l2(img.cpu().numpy(), img_ref.numpy()) <= tol
+    assert np.abs(logit.cpu().numpy() - logit_ref.numpy()).max() <= ltol * max(1.0, np.abs(logit_ref.numpy()).max())
+    assert rel_l2(grad.cpu().numpy(), grad_ref.numpy()) <= gtol
+    assert np.array_equal(logit.cpu().numpy(), logit2.cpu().numpy())
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("arch_name,B,K,method,gain", [("mnist", 6, 5, "momentum", 3.0), ("mnist", 3, 3, "sgd", 3.0),
+                                                        ("dcgan32_l2", 4, 4, "momentum", 2.5),
+                                                        ("dcgan64_l1", 2, 3, "momentum", 2.5)])
+def test_build_refiner_matches_oracle(cgs_lib, cuda_device, arch_name, B, K, method, gain, math):
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 9, gain, cuda_device)
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(2)))
+    o = gr.build_refiner(h0, arch, w, K, 0.1, method=method)
+    ref = Refiner(K, 0.1, method, math=math)
+    ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    out = ref.build_refiner(h0.to(cuda_device), None, "deterministic", keep_optimal_feature=True)
+    tol = 1e-4 if math == "fp32" else 5e-2
+    e_img = rel_l2(out.cpu().numpy(), o["refined"].numpy())
+    e_logit = np.abs(ref.optimal_logit.cpu().numpy() - o["optimal_logit"].numpy()).max()
+    e_feat = rel_l2(ref.current_feature.cpu().numpy(), o["final_feature"].numpy())
+    print(arch_name, math, "default", o["default_logit"].numpy(), "optimal", o["optimal_logit"].numpy(), "steps",
+          o["optimal_step"].numpy(), "| img rel %.2e logit abs %.2e final feature rel %.2e" % (e_img, e_logit, e_feat))
+    assert e_img <= tol and e_feat <= tol
+    assert e_logit <= tol * max(1.0, np.abs(o["optimal_logit"].numpy()).max())
+    assert np.abs(ref.default_logit.cpu().numpy() - o["default_logit"].numpy()).max() <= tol * 2
+    if math == "fp32":
+        assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
+    assert rel_l2(ref.optimal_feature.cpu().numpy(), o["optimal_feature"].numpy()) <= tol
+
+
+def test_probabilistic_mode_and_clip(cgs_lib, cuda_device):
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("mnist", 9, 3.0, cuda_device)
+    B, K = 7, 4
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(3)))
+    idx = np.array([0, 1, 2, 3, 4, 4, 0])        # value K keeps the proposal (collaborator.py:77,81-83)
+    o = gr.build_refiner(h0, arch, w, K, 0.1, mode="probabilistic", prob_indices=idx)
+    ref = Refiner(K, 0.1, math="fp32")
+    ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    out = ref.build_refiner(h0.to(cuda_device), None, "probabilistic", prob_indices=idx)
+    assert rel_l2(out.cpu().numpy(), o["refined"].numpy()) <= 1e-4
+    assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
+    # clipping (collaborator.py:69-70); a zero bound disables it (truthiness test, sic)
+    ref2 = Refiner(K, 0.1, math="fp32")
+    ref2.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    ref2.set_constraints(0.05, 0.8)
+    o2 = gr.build_refiner(h0, arch, w, K, 0.1, vmin=0.05, vmax=0.8)
+    out2 = ref2.build_refiner(h0.to(cuda_device), None)
+    assert rel_l2(out2.cpu().numpy(), o2["refined"].numpy()) <= 1e-4
+    assert float(ref2.current_feature.max()) <= 0.8 + 1e-6 and float(ref2.current_feature.min()) >= 0.05 - 1e-6
+    with pytest.raises(TypeError):
+        r3 = Refiner(K, 0.1, "ladam")
+        r3.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+        r3.build_refiner(h0.to(cuda_device), None)
+    with pytest.raises(NotImplementedError):
+        ref.build_refiner(h0.to(cuda_device), None, "greedy")
