@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("CGS_NVCC_EXTRA", "").split()
 
 
 def sources():

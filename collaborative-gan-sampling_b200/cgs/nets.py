@@ -153,15 +153,37 @@ def pack_layer(layer, w, b):
         m = m * valid.view(-1, 1).to(m.dtype)
         return m.t().contiguous()                                       # [rows, K]
 
-    w_fwd = gather(*pack_map(layer, False), True)
-    w_bwd = gather(*pack_map(layer, True), False)
+    def scatter(small_is_cout):
+        """rows = (ky*k + kx)*4 + small channel, K = the large channel count (cgs_pass_layout == 1)."""
+        k = layer["k"]
+        if layer["type"] == "deconv":            # [kh,kw,Cout,Cin], forward: small = cout, reduce over cin
+            m = w                                 # [k,k,cout,cin]
+        else:                                    # conv [kh,kw,Cin,Cout], backward: small = cin, reduce over cout
+            m = w                                 # [k,k,cin,cout]
+        small, big = m.shape[2], m.shape[3]
+        out = torch.zeros(k, k, 4, big)
+        out[:, :, :small, :] = m
+        return out.reshape(k * k * 4, big).contiguous()
+
+    lib = L.load()
+    d = _layer_desc(layer)
+    w_fwd = scatter(True) if lib.cgs_pass_layout(C.byref(d), 0) == 1 else gather(*pack_map(layer, False), True)
+    w_bwd = scatter(False) if lib.cgs_pass_layout(C.byref(d), 1) == 1 else gather(*pack_map(layer, True), False)
     return w_fwd, w_bwd, bias
+
+
+def round_tf32(t):
+    """Round-to-nearest (ties away, like cvt.rna.tf32.f32) to a 10-bit mantissa, so that the tensor core's operand
+    truncation is exact instead of a systematic shrink."""
+    i = t.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return torch.where(torch.isfinite(t), r, t)
 
 
 class PackedNet:
     """A chain of packed layers resident on one device + the cgs_net_desc that points at them."""
 
-    def __init__(self, layers, scope, weights, device):
+    def __init__(self, layers, scope, weights, device, math="tf32"):
         if len(layers) > L.MAX_LAYERS:
             raise ValueError("too many layers")
         self.layers = [dict(l) for l in layers]
@@ -173,6 +195,8 @@ class PackedNet:
         for i, layer in enumerate(layers):
             w, b = fold_layer(layer, scope, weights)
             wf, wb, bias = pack_layer(layer, w, b)
+            if math == "tf32" and wb is not None:       # GEMM layers only; the 1-logit head stays FP32
+                wf, wb = round_tf32(wf), round_tf32(wb)
             d = _layer_desc(layer)
             wf = wf.to(self.device)
             bias = bias.to(self.device)
@@ -192,11 +216,15 @@ class PackedNet:
 class NetSpec:
     """What ``Refiner.set_env`` receives in place of the reference's TF callables."""
 
-    def __init__(self, arch, weights, device="cuda", role=None):
+    def __init__(self, arch, weights, device="cuda", role=None, math="tf32"):
+        """math='tf32': tensor-core path (weights pre-rounded to TF32); math='fp32': exact-FP32 SIMT path."""
+        if math not in L.MATH_IDS:
+            raise ValueError("math must be 'tf32' or 'fp32'")
         self.arch = arch
+        self.math = math
         self.device = torch.device(device)
-        self.gtail = PackedNet(arch["gtail"], "generator", weights, self.device)
-        self.d = PackedNet(arch["d"], "discriminator", weights, self.device)
+        self.gtail = PackedNet(arch["gtail"], "generator", weights, self.device, math)
+        self.d = PackedNet(arch["d"], "discriminator", weights, self.device, math)
         self.role = role
 
     @property

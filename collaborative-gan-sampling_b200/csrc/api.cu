@@ -36,3 +36,9 @@ namespace cgs { long long launches_total(); }
 extern "C" long long cgs_launch_count(void) { return cgs::launches_total(); }
 extern "C" int cgs_version(void) { return CGS_ABI_VERSION; }
 extern "C" const char* cgs_last_error(void) { return cgs::error_buffer(); }
+
+namespace cgs { int debug_trace_read(unsigned long long* out, int cap); }
+// Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when CGS_DEBUG has bit 256 set.
+extern "C" __attribute__((visibility("default"))) int cgs_debug_trace(unsigned long long* out_host, int capacity) {
+  return cgs::debug_trace_read(out_host, capacity);
+}

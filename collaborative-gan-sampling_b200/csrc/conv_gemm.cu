@@ -1,12 +1,14 @@
 // tcgen05 / TMEM implicit-GEMM kernel (TF32 inputs, FP32 accumulate) + an FP32 SIMT twin used by the
 // parity tests and as the exact-FP32 mode.  See conv_gemm.cuh for the contraction it computes.
 //
-// CTA = 10 warps, persistent over output tiles (128 rows x BN channels):
-//   warps 0-3  epilogue: tcgen05.ld the accumulator (TMEM lane = row), fused bias/activation/derivative/
-//              momentum update, vectorised global stores
-//   warps 4-7  A producers: cp.async gather of 128 rows x 128 B per K block into SWIZZLE_128B smem
-//   warp  8    MMA issuer (one elected lane): 4 x tcgen05.mma.kind::tf32 (K=8 each) per K block
-//   warp  9    TMA producer for the weight tile (BN rows x 128 B, SWIZZLE_128B)
+// CTA = 14 warps, persistent over output tiles (128 rows x BN channels):
+//   warps 0-3   epilogue: tcgen05.ld the accumulator (TMEM lane = row), transpose through padded smem so that
+//               global loads/stores are 128-byte row segments, fused bias/activation/derivative/momentum update
+//   warps 4-11  A producers: cp.async gather of 128 rows x 128 B per K block into SWIZZLE_128B smem; per tile
+//               each thread precomputes its 4 row bases + tap-validity bit masks, per K block it only adds a
+//               warp-uniform tap offset (the per-K-block instruction count, not bandwidth, bounds this role)
+//   warp  12    MMA issuer (one elected lane): 4 x tcgen05.mma.kind::tf32 (K=8 each) per K block
+//   warp  13    TMA producer for the weight tile (BN rows x 128 B, SWIZZLE_128B)
 // Pipelines: full/empty mbarriers per smem stage, tmem_full/tmem_empty per accumulator buffer
 // (2 x BN TMEM columns, so the epilogue of tile i overlaps the main loop of tile i+1).
 #include "conv_gemm.cuh"
@@ -14,30 +16,43 @@
 #include "common.h"
 
 #include <cuda.h>
+#include <cstdlib>
 
 namespace cgs {
+
+// ---- optional event trace of CTA 0 (CGS_DEBUG bit 256): (role, event, index, clock) records for pipeline analysis
+__device__ unsigned long long g_trace[16384];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace(const ConvGemmParams& p, int role, int ev, unsigned idx) {
+  // fixed slot per (role, event, index): a plain store, no atomics, so the traced thread is barely perturbed
+  if ((p.debug & 256) && blockIdx.x == 0 && idx < 1024) {
+    const unsigned slot = ((unsigned)(role * 4 + ev) << 10) + idx;
+    g_trace[slot & 16383] = ((unsigned long long)role << 60) | ((unsigned long long)ev << 56) |
+                            ((unsigned long long)(idx & 0xffffff) << 32) | (unsigned long long)(unsigned)clock64();
+  }
+}
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                       // floats per K block = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 8;
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;       // 12
+constexpr int kTmaWarp = kMmaWarp + 1;                 // 13
+constexpr int kThreads = (kTmaWarp + 1) * 32;          // 448
+constexpr int kRowsPerThread = BM / (kProdWarps * 4);  // 4
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int EPI_PITCH = 36;                // floats per staged row (16-byte aligned, conflict-free for LDS/STS.128)
+constexpr int EPI_STAGE_BYTES = kEpiWarps * 32 * EPI_PITCH * 4;   // 18 KB
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int LAG = STAGES / 2;     // cp.async groups kept in flight per producer thread
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-struct RowInfo {
-  int base;   // element offset of pixel (j*S, i*S) of image b; -1 if the row is past M
-  int y0, x0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -49,7 +64,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* smem_epi = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
@@ -61,17 +77,17 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads + 1);
+      mbar_init(&full_bar[s], (p.debug & 128) ? kProdWarps + 1 : kProdWarps * 32 + 1);   // async arrive of every producer thread + the TMA thread
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-  if (warp == 9 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_w);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -79,137 +95,165 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   const int tiles_per_class = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_per_class * p.nclasses;
+  const int per_img = p.MH * p.MW;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= kEpiWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------ A producers
-    const int pw = warp - 4;
+    const int pw = warp - kEpiWarps;
     const int chunk = lane & 7;           // 16-byte chunk inside the 128-byte row
     const int rsub = lane >> 3;           // 0..3
     const uint32_t smem_a_u32 = smem_u32(smem_a);
     const bool pixel_mode = (p.cblocks == 0);
-    uint32_t it_global = 0;               // K blocks issued by this thread (== commit groups)
+    uint32_t soff[kRowsPerThread];        // swizzled smem offset of (row, chunk) inside a stage
+#pragma unroll
+    for (int it = 0; it < kRowsPerThread; ++it) {
+      const int r = pw * (4 * kRowsPerThread) + it * 4 + rsub;
+      soff[it] = r * 128 + ((chunk ^ (r & 7)) << 4);
+    }
+    uint32_t it_global = 0;               // K blocks issued by this thread
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ci = tile / tiles_per_class;
       const int rem = tile - ci * tiles_per_class;
       const int m_tile = rem / p.n_tiles;
       const GemmClass& gc = p.cls[ci];
-      RowInfo ri[8];
+      const int nkx = gc.nkx;
+      const int nky = gc.ntaps / nkx;
+      int rbase[kRowsPerThread];
+      uint32_t vmask[kRowsPerThread];     // bit t set <=> tap t of this row lies inside the image
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = pw * 32 + it * 4 + rsub;
+      for (int it = 0; it < kRowsPerThread; ++it) {
+        const int r = pw * (4 * kRowsPerThread) + it * 4 + rsub;
         const int m = m_tile * BM + r;
+        rbase[it] = 0;
+        vmask[it] = 0;
         if (m < p.M) {
-          const int per_img = p.MH * p.MW;
           const int b = m / per_img;
           const int q = m - b * per_img;
           const int j = q / p.MW;
           const int i = q - j * p.MW;
-          ri[it].y0 = j * p.S;
-          ri[it].x0 = i * p.S;
-          ri[it].base = ((b * p.IH + ri[it].y0) * p.IW + ri[it].x0) * p.Cs;
-        } else {
-          ri[it].base = -1;
-          ri[it].y0 = 0;
-          ri[it].x0 = 0;
+          const int y0 = j * p.S, x0 = i * p.S;
+          rbase[it] = ((b * p.IH + y0) * p.IW + x0) * p.Cs;
+          uint32_t mx = 0;
+          for (int tx = 0; tx < nkx; ++tx)
+            if ((unsigned)(x0 + gc.dx[tx]) < (unsigned)p.IW) mx |= 1u << tx;
+          uint32_t vm = 0;
+          for (int ty = 0; ty < nky; ++ty)
+            if ((unsigned)(y0 + gc.dy[ty * nkx]) < (unsigned)p.IH) vm |= mx << (ty * nkx);
+          vmask[it] = vm;
         }
       }
+      int t = 0, cb = 0;                  // block mode: current tap / channel block
+      int tap_off = pixel_mode ? 0 : (gc.dy[0] * p.IW + gc.dx[0]) * p.Cs;
       for (int kb = 0; kb < gc.nkb; ++kb, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        int dy, dx, coff;
-        bool tap_ok = true;
+        int off, tt;
         if (pixel_mode) {
-          const int t = kb * 8 + chunk;   // one tap (4 channels = 16 B) per chunk
-          tap_ok = t < gc.ntaps;
-          dy = tap_ok ? gc.dy[t] : 0;
-          dx = tap_ok ? gc.dx[t] : 0;
-          coff = 0;
+          tt = kb * 8 + chunk;            // one tap (4 channels = 16 B) per chunk
+          const bool tap_ok = tt < gc.ntaps;
+          off = tap_ok ? (gc.dy[tt] * p.IW + gc.dx[tt]) * p.Cs : 0;
+          if (!tap_ok) tt = 31;           // bit 31 is never set (ntaps <= 25)
         } else {
-          const int t = kb / p.cblocks;
-          const int cb = kb - t * p.cblocks;
-          dy = gc.dy[t];
-          dx = gc.dx[t];
-          coff = cb * BK + chunk * 4;
+          tt = t;
+          off = tap_off + cb * BK + chunk * 4;
         }
-        const int tap_off = (dy * p.IW + dx) * p.Cs + coff;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (pw == 0 && lane == 0) trace(p, 0, 0, it_global);
         const uint32_t stage_base = smem_a_u32 + s * A_STAGE_BYTES;
+        if (!(p.debug & 1)) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = pw * 32 + it * 4 + rsub;
-          const bool ok = tap_ok && ri[it].base >= 0 && (unsigned)(ri[it].y0 + dy) < (unsigned)p.IH &&
-                          (unsigned)(ri[it].x0 + dx) < (unsigned)p.IW;
-          const float* src = ok ? p.in + (ri[it].base + tap_off) : p.in;
-          const uint32_t dst = stage_base + r * 128 + ((chunk ^ (r & 7)) << 4);
-          cp_async_16(dst, src, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (it_global >= (uint32_t)C::LAG) {
-          cp_async_wait<C::LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[(it_global - C::LAG) % C::STAGES]);
-        }
-      }
-    }
-    // drain: the last min(LAG, it_global) groups have not been published yet
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    const uint32_t pending = it_global < (uint32_t)C::LAG ? it_global : (uint32_t)C::LAG;
-    for (uint32_t g = it_global - pending; g < it_global; ++g) mbar_arrive(&full_bar[g % C::STAGES]);
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ TMA producer (weights)
-    if (lane == 0) {
-      const uint32_t smem_b_u32 = smem_u32(smem_b);
-      uint32_t it_global = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ci = tile / tiles_per_class;
-        const int rem = tile - ci * tiles_per_class;
-        const int n_tile = rem % p.n_tiles;
-        const GemmClass& gc = p.cls[ci];
-        for (int kb = 0; kb < gc.nkb; ++kb, ++it_global) {
-          const int s = it_global % C::STAGES;
-          const uint32_t ph = (it_global / C::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
-          tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], gc.k0 + kb * BK, n_tile * BN);
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      const uint32_t smem_a_u32 = smem_u32(smem_a);
-      const uint32_t smem_b_u32 = smem_u32(smem_b);
-      uint32_t it_global = 0;
-      uint32_t tile_count = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
-        const int ci = tile / tiles_per_class;
-        const int nkb = p.cls[ci].nkb;
-        const uint32_t acc = tile_count & 1;
-        const uint32_t acc_ph = (tile_count >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it_global) {
-          const int s = it_global % C::STAGES;
-          const uint32_t ph = (it_global / C::STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tcgen05_fence_after();
-          const uint64_t da = make_smem_desc_sw128(smem_a_u32 + s * A_STAGE_BYTES);
-          const uint64_t db = make_smem_desc_sw128(smem_b_u32 + s * C::B_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // +32 bytes per K=8 step inside the 128-byte swizzle row (address field is in 16-byte units)
-            umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int it = 0; it < kRowsPerThread; ++it) {
+            const bool ok = (vmask[it] >> tt) & 1u;
+            cp_async_16(stage_base + soff[it], p.in + (ok ? rbase[it] + off : 0), ok ? 16u : 0u);
           }
-          umma_commit(&empty_bar[s]);          // smem stage reusable once these MMAs have read it
         }
-        umma_commit(&tmem_full_bar[acc]);      // accumulator complete
+        // the copies of this thread arrive on the stage's full barrier when they land: no wait on the issue side,
+        // so up to STAGES K blocks of gathers are in flight per CTA
+        if (p.debug & 128) { __syncwarp(); if (lane == 0) mbar_arrive(&full_bar[s]); } else
+        cp_async_mbar_arrive_noinc(&full_bar[s]);
+        if (pw == 0 && lane == 0) trace(p, 0, 1, it_global);
+        if (!pixel_mode && ++cb == p.cblocks) {
+          cb = 0;
+          ++t;
+          if (t < gc.ntaps) tap_off = (gc.dy[t] * p.IW + gc.dx[t]) * p.Cs;
+        }
+      }
+    }
+  } else if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA producer (weights)
+    // whole warp walks the loop (uniform control flow); one elected lane issues
+    const uint32_t smem_b_u32 = smem_u32(smem_b);
+    uint32_t it_global = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ci = tile / tiles_per_class;
+      const int rem = tile - ci * tiles_per_class;
+      const int n_tile = rem % p.n_tiles;
+      const int k0 = p.cls[ci].k0;
+      const int nkb = p.cls[ci].nkb;
+      for (int kb = 0; kb < nkb; ++kb, ++it_global) {
+        const int s = it_global % C::STAGES;
+        const uint32_t ph = (it_global / C::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          trace(p, 1, 0, it_global);
+          if (p.debug & 2) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
+            tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], k0 + kb * BK, n_tile * BN);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    // whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem_a));
+    const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem_b));
+    uint32_t it_global = 0;
+    uint32_t tile_count = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
+      const int ci = tile / tiles_per_class;
+      const int nkb = p.cls[ci].nkb;
+      const uint32_t acc = tile_count & 1;
+      const uint32_t acc_ph = (tile_count >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it_global) {
+        const int s = it_global % C::STAGES;
+        const uint32_t ph = (it_global / C::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          trace(p, 2, 0, it_global);
+          // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          if (!(p.debug & 64)) fence_proxy_async_smem();
+          // descriptor address field is in 16-byte units: + stage offset, + 32 bytes per K=8 step
+          const uint64_t da = da0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
+          const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete
+          trace(p, 2, 1, it_global);
+        }
+        __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3)
+    constexpr int CH = BN >= 32 ? 32 : 16;         // accumulator columns per TMEM load
+    constexpr int Q = CH / 4;                      // float4 per staged row
+    constexpr int ROWS_PER_PASS = 32 / Q;          // rows covered by one warp-wide 16-byte access
+    float* stage = smem_epi + warp * 32 * EPI_PITCH;
+    const int c4 = lane % Q;
+    const int rsub = lane / Q;
     uint32_t tile_count = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
       const int ci = tile / tiles_per_class;
@@ -219,51 +263,59 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const GemmClass& gc = p.cls[ci];
       const uint32_t acc = tile_count & 1;
       const uint32_t acc_ph = (tile_count >> 1) & 1;
-      const int r = warp * 32 + lane;
-      const int m = m_tile * BM + r;
-      size_t row_off = 0;
-      const bool row_ok = m < p.M;
-      if (row_ok) {
-        const int per_img = p.MH * p.MW;
+      const int m = m_tile * BM + warp * 32 + lane;
+      int row_off = -1;                            // element offset of this lane's row in out / aux / mom
+      if (m < p.M) {
         const int b = m / per_img;
         const int q = m - b * per_img;
         const int j = q / p.MW;
         const int i = q - j * p.MW;
-        row_off = ((size_t)(b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
+        row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
       }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
+      if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(warp * 32) << 16);
-      constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t v[CH];
         if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, v); else tmem_ld_32x32b_x16(taddr + c0, v);
         tmem_ld_wait();
+        if (c0 + CH >= BN) {
+          // all TMEM reads of this accumulator are done: hand it back before the global-memory part
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
+        }
         const int nbase = n_tile * BN + c0;
-        if (row_ok && nbase < p.ON) {
+        if (nbase >= p.ON || (p.debug & 16)) continue;        // warp-uniform
+        // lane = row: stage 32 rows x CH columns, then re-read with lane = (row group, 16-byte column)
 #pragma unroll
-          for (int q4 = 0; q4 < CH; q4 += 4) {
-            const int n = nbase + q4;
-            if (n < p.ON) {          // ON is a multiple of 4
-              float4 o;
-              o.x = epilogue_value(p, row_off + n + 0, n + 0, __uint_as_float(v[q4 + 0]));
-              o.y = epilogue_value(p, row_off + n + 1, n + 1, __uint_as_float(v[q4 + 1]));
-              o.z = epilogue_value(p, row_off + n + 2, n + 2, __uint_as_float(v[q4 + 2]));
-              o.w = epilogue_value(p, row_off + n + 3, n + 3, __uint_as_float(v[q4 + 3]));
-              *reinterpret_cast<float4*>(p.out + row_off + n) = o;
-            }
+        for (int q4 = 0; q4 < Q; ++q4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + q4 * 4) =
+              make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                          __uint_as_float(v[4 * q4 + 3]));
+        __syncwarp();
+        const int n = nbase + c4 * 4;
+#pragma unroll
+        for (int rp = 0; rp < 32; rp += ROWS_PER_PASS) {
+          const int rr = rp + rsub;
+          const int ro = __shfl_sync(0xffffffffu, row_off, rr);
+          if (ro >= 0 && n < p.ON) {               // ON is a multiple of 4
+            const float4 a = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + c4 * 4);
+            *reinterpret_cast<float4*>(p.out + ro + n) = epilogue4(p, ro + n, n, a);
           }
         }
+        __syncwarp();
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if (warp == 0 && lane == 0) trace(p, 3, 2, tile_count);
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,13 +354,9 @@ conv_gemm_simt_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
         }
       }
     }
-    const size_t row_off = ((size_t)(b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
-    float4 o;
-    o.x = epilogue_value(p, row_off + ng * 4 + 0, ng * 4 + 0, acc[0]);
-    o.y = epilogue_value(p, row_off + ng * 4 + 1, ng * 4 + 1, acc[1]);
-    o.z = epilogue_value(p, row_off + ng * 4 + 2, ng * 4 + 2, acc[2]);
-    o.w = epilogue_value(p, row_off + ng * 4 + 3, ng * 4 + 3, acc[3]);
-    *reinterpret_cast<float4*>(p.out + row_off + ng * 4) = o;
+    const int row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
+    *reinterpret_cast<float4*>(p.out + row_off + ng * 4) =
+        epilogue4(p, row_off + ng * 4, ng * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
   }
 }
 
@@ -354,6 +402,11 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("CGS_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.n_tiles = (p.N + BN - 1) / BN;
   p.m_tiles = (p.M + BM - 1) / BM;
   static int num_sms = 0;
@@ -390,6 +443,15 @@ int validate(const ConvGemmParams& p, int w_cols) {
 }
 
 }  // namespace
+
+int debug_trace_read(unsigned long long* out, int cap) {
+  cudaDeviceSynchronize();
+  const int n = cap < 16384 ? cap : 16384;
+  cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long));
+  static unsigned long long zeros[16384];
+  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+  return n;
+}
 
 int launch_conv_gemm_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   if (int rc = validate(p, w_cols)) return rc;

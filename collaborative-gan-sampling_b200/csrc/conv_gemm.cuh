@@ -30,7 +30,8 @@ constexpr int kMaxClasses = 4;
 struct GemmClass {
   int k0;      // first K element of this class inside the packed weight matrix
   int nkb;     // K blocks (32 floats) of this class
-  int ntaps;   // taps of this class
+  int ntaps;   // taps of this class = nky * nkx, tap t = ty * nkx + tx, dy depends on ty only, dx on tx only
+  int nkx;
   int oy0, ox0;
   signed char dy[kMaxTaps];
   signed char dx[kMaxTaps];
@@ -54,6 +55,8 @@ struct ConvGemmParams {
   int epi, act;
   int first, clip, sgd;
   float rate, alpha, vmin, vmax;
+  int round_out;      // round results to TF32 (RN) because the next consumer is a kind::tf32 MMA
+  int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
   GemmClass cls[kMaxClasses];
 };
 
@@ -75,25 +78,51 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
   }
 }
 
-// One output element.  `off` = element offset of (row, n) in out / aux / mom.
-__device__ __forceinline__ float epilogue_value(const ConvGemmParams& p, size_t off, int n, float acc) {
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Four consecutive output channels.  `off` = element offset of (row, n) in out / aux / mom (multiple of 4).
+__device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, int n, float4 a) {
+  float4 o = a;
   if (p.epi == EPI_FWD) {
-    return act_apply(acc + (p.bias ? __ldg(p.bias + n) : 0.f), p.act);
+    const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x = act_apply(a.x + b.x, p.act);
+    o.y = act_apply(a.y + b.y, p.act);
+    o.z = act_apply(a.z + b.z, p.act);
+    o.w = act_apply(a.w + b.w, p.act);
   } else if (p.epi == EPI_BWD) {
-    return acc * act_grad_from_output(__ldg(p.aux + off), p.act);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(p.aux + off));
+    o.x = a.x * act_grad_from_output(y.x, p.act);
+    o.y = a.y * act_grad_from_output(y.y, p.act);
+    o.z = a.z * act_grad_from_output(y.z, p.act);
+    o.w = a.w * act_grad_from_output(y.w, p.act);
   } else if (p.epi == EPI_UPDATE) {
-    float m;
-    if (p.sgd) {
-      m = p.rate * acc;                                            // policy.py:28
-    } else {
-      m = p.first ? p.rate * acc : p.alpha * p.mom[off] + p.rate * acc;   // policy.py:32-35
-      p.mom[off] = m;
+    // sampling/policy.py:27-37; separately rounded multiplies / adds like the reference's un-fused TF ops
+    float4 m;
+    m.x = __fmul_rn(p.rate, a.x); m.y = __fmul_rn(p.rate, a.y); m.z = __fmul_rn(p.rate, a.z); m.w = __fmul_rn(p.rate, a.w);
+    if (!p.sgd) {
+      if (!p.first) {
+        const float4 mo = *reinterpret_cast<const float4*>(p.mom + off);
+        m.x = __fadd_rn(__fmul_rn(p.alpha, mo.x), m.x);
+        m.y = __fadd_rn(__fmul_rn(p.alpha, mo.y), m.y);
+        m.z = __fadd_rn(__fmul_rn(p.alpha, mo.z), m.z);
+        m.w = __fadd_rn(__fmul_rn(p.alpha, mo.w), m.w);
+      }
+      *reinterpret_cast<float4*>(p.mom + off) = m;
     }
-    float h = p.out[off] - m;                                      // policy.py:28,36
-    if (p.clip) h = fminf(fmaxf(h, p.vmin), p.vmax);               // collaborator.py:69-70
-    return h;
+    const float4 h = *reinterpret_cast<const float4*>(p.out + off);
+    o.x = __fsub_rn(h.x, m.x); o.y = __fsub_rn(h.y, m.y); o.z = __fsub_rn(h.z, m.z); o.w = __fsub_rn(h.w, m.w);
+    if (p.clip) {                                                    // collaborator.py:69-70
+      o.x = fminf(fmaxf(o.x, p.vmin), p.vmax); o.y = fminf(fmaxf(o.y, p.vmin), p.vmax);
+      o.z = fminf(fmaxf(o.z, p.vmin), p.vmax); o.w = fminf(fmaxf(o.w, p.vmin), p.vmax);
+    }
+    return o;
   }
-  return acc;
+  if (p.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+  return o;
 }
 
 // host launchers (conv_gemm.cu)

@@ -63,6 +63,7 @@ void fill_strided(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) {
   g.k0 = 0;
   g.oy0 = g.ox0 = 0;
   g.ntaps = k * k;
+  g.nkx = k;
   for (int ky = 0; ky < k; ++ky)
     for (int kx = 0; kx < k; ++kx) {
       g.dy[ky * k + kx] = (signed char)(ky - pad_y);
@@ -112,6 +113,7 @@ void fill_transposed(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) 
         }
       }
       g.ntaps = t;
+      g.nkx = ntap(px, pad_x);
       g.nkb = t * p.cblocks;
       k0 += t * cin_k;
     }
@@ -147,6 +149,7 @@ int make_forward_params(const cgs_layer_desc& L, int64_t B, const float* x, floa
   } else {
     p.nclasses = 1;
     p.cls[0].ntaps = 1;
+    p.cls[0].nkx = 1;
     p.cblocks = L.cin / 32;
     p.cls[0].nkb = p.cblocks;
     p.S = 1;
@@ -188,6 +191,7 @@ int make_backward_params(const cgs_layer_desc& L, int64_t B, const float* dy, fl
     if (L.cout % 32) return set_error(CGS_ERR_UNSUPPORTED, "fc output size %d must be a multiple of 32", L.cout);
     p.nclasses = 1;
     p.cls[0].ntaps = 1;
+    p.cls[0].nkx = 1;
     p.cblocks = L.cout / 32;
     p.cls[0].nkb = p.cblocks;
     p.S = 1;
@@ -202,10 +206,168 @@ int make_backward_params(const cgs_layer_desc& L, int64_t B, const float* dy, fl
   return CGS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Scatter formulation for transposed-type passes with <= 4 output channels (deconv -> image, conv1 data-gradient).
+// The gather form would re-read every input pixel k^2/4 * 4 times for a 1..3-wide output; instead
+//   stage 1  col[b,iy,ix,(ky,kx,c)] = sum_ci in[b,iy,ix,ci] * W[(ky,kx,c)][ci]     one GEMM, input read once
+//   stage 2  out[b,y,x,c] = epi( sum_{(ky,kx): y = 2 iy + ky - p, x = 2 ix + kx - p} col[b,iy,ix,(ky,kx,c)] )
+// Same MACs as the true-tap count; stage 2 is a small memory-bound kernel with the fused epilogue.
+// ---------------------------------------------------------------------------------------------
+bool use_scatter(const cgs_layer_desc& L, bool backward) {
+  return (L.type == CGS_LAYER_DECONV && !backward && L.cout <= 4) || (L.type == CGS_LAYER_CONV && backward && L.cin <= 4);
+}
+inline int scatter_cols(const cgs_layer_desc& L) { return L.k * L.k * 4; }      // col row pitch (floats)
+
+size_t scatter_col_elems(const cgs_layer_desc& L, bool backward) {
+  if (!use_scatter(L, backward)) return 0;
+  const LayerShape s = layer_shape(L);
+  const size_t pixels = backward ? (size_t)s.hout * s.wout : (size_t)L.hin * L.win;   // stage-1 rows per sample
+  return pixels * scatter_cols(L);
+}
+
+// stage 1 as a 1-tap "fc over pixels": rows = B * pixels, K = big channel count, N = k*k*4
+int make_scatter_gemm_params(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* col,
+                             ConvGemmParams& p) {
+  if (int rc = check_layer(L)) return rc;
+  std::memset(&p, 0, sizeof(p));
+  const LayerShape s = layer_shape(L);
+  const int kch = backward ? L.cout : L.cin;                   // reduced (big) channel count
+  const int64_t pixels = backward ? (int64_t)s.hout * s.wout : (int64_t)L.hin * L.win;
+  p.in = in;
+  p.out = col;
+  p.epi = EPI_RAW;
+  p.N = scatter_cols(L);
+  p.ON = scatter_cols(L);
+  p.OH = p.OW = 1;
+  p.IH = p.IW = 1;
+  p.Cs = kch;
+  p.nclasses = 1;
+  p.cls[0].ntaps = 1;
+  p.cls[0].nkx = 1;
+  p.cblocks = kch / 32;
+  p.cls[0].nkb = p.cblocks;
+  p.S = 1;
+  p.os = 1;
+  p.MH = p.MW = 1;
+  if (B * pixels >= (1ll << 31) / p.ON) return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit indexing; split the batch");
+  p.M = (int)(B * pixels);
+  return CGS_OK;
+}
+
+struct Col2imParams {
+  const float* col;
+  float* out;
+  const float* bias;
+  const float* aux;
+  int IH, IW, OH, OW, k, pad_y, pad_x, pitch;
+  int epi, act, round_out;
+  long long pixels;      // B * OH * OW
+};
+
+__global__ void __launch_bounds__(256) col2im_kernel(const Col2imParams p) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.pixels;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.OW);
+    const long long t = idx / p.OW;
+    const int y = (int)(t % p.OH);
+    const long long b = t / p.OH;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < p.k; ++ky) {
+      const int ty = y + p.pad_y - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int iy = ty >> 1;
+      if (iy >= p.IH) continue;
+      for (int kx = 0; kx < p.k; ++kx) {
+        const int tx = x + p.pad_x - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ix = tx >> 1;
+        if (ix >= p.IW) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            p.col + ((b * p.IH + iy) * p.IW + ix) * p.pitch + (ky * p.k + kx) * 4));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    }
+    float4 o = a;
+    if (p.epi == EPI_FWD) {
+      const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = act_apply(a.x + bb.x, p.act); o.y = act_apply(a.y + bb.y, p.act);
+      o.z = act_apply(a.z + bb.z, p.act); o.w = act_apply(a.w + bb.w, p.act);
+    } else if (p.epi == EPI_BWD) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(p.aux + idx * 4));
+      o.x = a.x * act_grad_from_output(yv.x, p.act); o.y = a.y * act_grad_from_output(yv.y, p.act);
+      o.z = a.z * act_grad_from_output(yv.z, p.act); o.w = a.w * act_grad_from_output(yv.w, p.act);
+    }
+    if (p.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+    *reinterpret_cast<float4*>(p.out + idx * 4) = o;
+  }
+}
+
+struct PassEpi {
+  int epi = EPI_RAW;
+  int act = ACT_NONE;
+  const float* aux = nullptr;
+  int round_out = 0;
+  const ConvGemmParams* upd = nullptr;   // EPI_UPDATE fields
+};
+
 int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int math, cudaStream_t stream) {
   if (math == CGS_MATH_FP32_SIMT) return launch_conv_gemm_simt(p, w, rows, cols, stream);
   if (math == CGS_MATH_TF32_TENSOR) return launch_conv_gemm_tc(p, w, rows, cols, stream);
   return set_error(CGS_ERR_INVALID, "unknown math mode %d", math);
+}
+
+// One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
+int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
+             float* col, int math, cudaStream_t st) {
+  const float* w = backward ? L.w_bwd : L.w_fwd;
+  const int rows = backward ? L.rows_bwd : L.rows_fwd;
+  const int cols = backward ? L.kcols_bwd : L.kcols_fwd;
+  if (!w) return set_error(CGS_ERR_INVALID, "layer has no packed %s weights", backward ? "backward" : "forward");
+  if (use_scatter(L, backward)) {
+    if (!col) return set_error(CGS_ERR_WORKSPACE, "scatter pass needs a column workspace");
+    if (rows != scatter_cols(L)) return set_error(CGS_ERR_INVALID, "weights of this pass must be in scatter layout (%d rows)", scatter_cols(L));
+    ConvGemmParams p;
+    if (int rc = make_scatter_gemm_params(L, backward, B, in, col, p)) return rc;
+    if (int rc = launch_gemm(p, w, rows, cols, math, st)) return rc;
+    const LayerShape s = layer_shape(L);
+    Col2imParams c;
+    c.col = col;
+    c.out = out;
+    c.bias = (e.epi == EPI_FWD) ? L.bias : nullptr;
+    c.aux = e.aux;
+    c.k = L.k;
+    c.pitch = scatter_cols(L);
+    c.epi = e.epi;
+    c.act = e.act;
+    c.round_out = e.round_out;
+    if (!backward) {           // deconv forward: col over the input grid, out = 2x grid
+      c.IH = L.hin; c.IW = L.win; c.OH = s.hout; c.OW = s.wout;
+      c.pad_y = same_pad_before(s.hout, L.k); c.pad_x = same_pad_before(s.wout, L.k);
+    } else {                   // conv data-gradient: col over the conv-output grid, out = conv-input grid
+      c.IH = s.hout; c.IW = s.wout; c.OH = L.hin; c.OW = L.win;
+      c.pad_y = same_pad_before(L.hin, L.k); c.pad_x = same_pad_before(L.win, L.k);
+    }
+    c.pixels = (long long)B * c.OH * c.OW;
+    long long blocks = (c.pixels + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    col2im_kernel<<<(int)blocks, 256, 0, st>>>(c); count_launch();
+    return check_launch("col2im_kernel");
+  }
+  ConvGemmParams p;
+  if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) return rc;
+  if (!backward) p.bias = L.bias;
+  p.epi = e.epi;
+  p.act = e.act;
+  p.aux = e.aux;
+  p.round_out = e.round_out;
+  if (e.upd) {
+    p.epi = EPI_UPDATE;
+    p.mom = e.upd->mom; p.first = e.upd->first; p.sgd = e.upd->sgd; p.rate = e.upd->rate; p.alpha = e.upd->alpha;
+    p.clip = e.upd->clip; p.vmin = e.upd->vmin; p.vmax = e.upd->vmax;
+    p.round_out = 0;
+  }
+  return launch_gemm(p, w, rows, cols, math, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,6 +399,7 @@ struct HeadParams {
   int mode;
   unsigned char* done;  // early-exit flags [B] or nullptr
   float exit_logit;
+  int round_out;        // round dpre to TF32 (RN): it feeds a kind::tf32 MMA
 };
 
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
@@ -298,6 +461,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
       o.y = dl * ww.y * act_grad_from_output(a.y, p.act);
       o.z = dl * ww.z * act_grad_from_output(a.z, p.act);
       o.w = dl * ww.w * act_grad_from_output(a.w, p.act);
+      if (p.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
       *reinterpret_cast<float4*>(d + k) = o;
     }
   }
@@ -323,6 +487,7 @@ struct Chain {
   int n_gtail;
   cgs_layer_desc head;
   size_t max_elems;
+  size_t col_elems;              // per-sample elements of the scatter column buffer (0 if unused)
 };
 
 static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& c) {
@@ -339,8 +504,13 @@ static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& 
   const cgs_layer_desc& L0 = c.layers[0];
   c.act_elems[0] = (size_t)L0.hin * L0.win * cstride(L0.cin);
   c.max_elems = c.act_elems[0];
+  c.col_elems = 0;
   for (int i = 0; i < c.n; ++i) {
     if (int rc = check_layer(c.layers[i])) return rc;
+    for (int bw = 0; bw < 2; ++bw) {
+      const size_t ce = scatter_col_elems(c.layers[i], bw != 0);
+      if (ce > c.col_elems) c.col_elems = ce;
+    }
     const LayerShape s = layer_shape(c.layers[i]);
     c.act_elems[i + 1] = (size_t)s.hout * s.wout * s.cs_out;
     if (c.act_elems[i + 1] > c.max_elems) c.max_elems = c.act_elems[i + 1];
@@ -363,6 +533,7 @@ struct Workspace {
   float* act[2 * CGS_MAX_LAYERS + 1];
   float* g[2];
   float* mom;
+  float* col;
   float* cur_logit;
   unsigned char* done;
   size_t total;
@@ -377,6 +548,7 @@ static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
   w.g[0] = (float*)take((size_t)B * c.max_elems * 4);
   w.g[1] = (float*)take((size_t)B * c.max_elems * 4);
   w.mom = (float*)take((size_t)B * c.act_elems[0] * 4);
+  w.col = c.col_elems ? (float*)take((size_t)B * c.col_elems * 4) : nullptr;
   w.cur_logit = (float*)take((size_t)B * 4);
   w.done = (unsigned char*)take((size_t)B);
   w.total = off;
@@ -384,9 +556,13 @@ static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
 
 static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st) {
   for (int i = 0; i < c.n; ++i) {
-    ConvGemmParams p;
-    if (int rc = make_forward_params(c.layers[i], B, w.act[i], w.act[i + 1], p)) return rc;
-    if (int rc = launch_gemm(p, c.layers[i].w_fwd, c.layers[i].rows_fwd, c.layers[i].kcols_fwd, math, st)) return rc;
+    PassEpi e;
+    e.epi = EPI_FWD;
+    e.act = c.layers[i].act;
+    // TF32 path: activations that feed another MMA are rounded to TF32 (RN) where they are produced, so the
+    // tensor core's operand truncation is exact; the image (returned to the caller) and the head input stay FP32
+    e.round_out = (math == CGS_MATH_TF32_TENSOR) && (i != c.n_gtail - 1) && (i != c.n - 1);
+    if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st)) return rc;
   }
   return CGS_OK;
 }
@@ -397,25 +573,17 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
                         float* grad_out, cudaStream_t st) {
   int cur = 0;
   for (int i = c.n - 1; i >= 0; --i) {
-    ConvGemmParams p;
     float* dst = (i == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
-    if (int rc = make_backward_params(c.layers[i], B, w.g[cur], dst, p)) return rc;
+    PassEpi e;
     if (i > 0) {
-      p.epi = EPI_BWD;
-      p.aux = w.act[i];
-      p.act = c.layers[i - 1].act;
-    } else if (upd) {
-      p.epi = EPI_UPDATE;
-      p.mom = upd->mom;
-      p.first = upd->first;
-      p.sgd = upd->sgd;
-      p.rate = upd->rate;
-      p.alpha = upd->alpha;
-      p.clip = upd->clip;
-      p.vmin = upd->vmin;
-      p.vmax = upd->vmax;
+      e.epi = EPI_BWD;
+      e.aux = w.act[i];
+      e.act = c.layers[i - 1].act;
+      e.round_out = (math == CGS_MATH_TF32_TENSOR);
+    } else {
+      e.upd = upd;
     }
-    if (int rc = launch_gemm(p, c.layers[i].w_bwd, c.layers[i].rows_bwd, c.layers[i].kcols_bwd, math, st)) return rc;
+    if (int rc = run_pass(c.layers[i], true, B, w.g[cur], dst, e, w.col, math, st)) return rc;
     cur ^= 1;
   }
   return CGS_OK;
@@ -480,6 +648,7 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   hp.prob_indices = prob_indices;
   hp.mode = cfg->mode;
   hp.exit_logit = cfg->exit_logit;
+  hp.round_out = (cfg->math == CGS_MATH_TF32_TENSOR);
   if (cfg->early_exit) {
     hp.done = w.done;
     cudaMemsetAsync(w.done, 0, (size_t)B, st);
@@ -533,6 +702,7 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   hp.best_logit = w.cur_logit;
   hp.best_step = w.mom;          // scratch (>= B floats)
   hp.step = -1;
+  hp.round_out = (math == CGS_MATH_TF32_TENSOR);
   hp.dpre = grad_out ? w.g[0] : nullptr;
   if (int rc = head_launch(c, w, B, hp, st)) return rc;
   cudaMemcpyAsync(logit_out, w.cur_logit, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
@@ -544,27 +714,49 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   return check_launch("cgs_forward_logits_and_grad");
 }
 
+extern "C" size_t cgs_layer_workspace_bytes(const cgs_layer_desc* L, int64_t B) {
+  if (!L || B < 0) return 0;
+  size_t ce = scatter_col_elems(*L, false);
+  const size_t cb = scatter_col_elems(*L, true);
+  if (cb > ce) ce = cb;
+  return ce * (size_t)B * 4 + 256;
+}
+
 extern "C" int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y,
-                                 cgs_stream_t stream) {
+                                 void* workspace, size_t workspace_bytes, cgs_stream_t stream) {
   if (int rc = require_sm100()) return rc;
   if (!L || !x || !y) return set_error(CGS_ERR_INVALID, "null argument");
-  ConvGemmParams p;
-  if (int rc = make_forward_params(*L, B, x, y, p)) return rc;
-  return launch_gemm(p, L->w_fwd, L->rows_fwd, L->kcols_fwd, math, (cudaStream_t)stream);
+  if (use_scatter(*L, false) && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(L, B)))
+    return set_error(CGS_ERR_WORKSPACE, "workspace too small");
+  PassEpi e;
+  e.epi = EPI_FWD;
+  e.act = L->act;
+  float* col = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  return run_pass(*L, false, B, x, y, e, col, math, (cudaStream_t)stream);
 }
 
 extern "C" int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, const float* dy, float* dx,
-                                  const float* x_fwd, int prev_act, cgs_stream_t stream) {
+                                  const float* x_fwd, int prev_act, void* workspace, size_t workspace_bytes,
+                                  cgs_stream_t stream) {
   if (int rc = require_sm100()) return rc;
   if (!L || !dy || !dx) return set_error(CGS_ERR_INVALID, "null argument");
-  ConvGemmParams p;
-  if (int rc = make_backward_params(*L, B, dy, dx, p)) return rc;
+  if (use_scatter(*L, true) && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(L, B)))
+    return set_error(CGS_ERR_WORKSPACE, "workspace too small");
+  PassEpi e;
   if (x_fwd && prev_act != CGS_ACT_NONE) {
-    p.epi = EPI_BWD;
-    p.aux = x_fwd;
-    p.act = prev_act;
+    e.epi = EPI_BWD;
+    e.aux = x_fwd;
+    e.act = prev_act;
   }
-  return launch_gemm(p, L->w_bwd, L->rows_bwd, L->kcols_bwd, math, (cudaStream_t)stream);
+  float* col = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  return run_pass(*L, true, B, dy, dx, e, col, math, (cudaStream_t)stream);
+}
+
+// Host-only: 0 = the pass uses the gather layout described by cgs_pack_map, 1 = scatter layout
+// (rows = (ky*k + kx)*4 + small channel, K = the large channel count; see "Scatter formulation" above).
+extern "C" int cgs_pass_layout(const cgs_layer_desc* L, int backward) {
+  if (!L) return set_error(CGS_ERR_INVALID, "null layer");
+  return use_scatter(*L, backward != 0) ? 1 : 0;
 }
 
 // Host-only: the K ordering of a layer's packed weight matrix, so the packer (cgs/pack.py) never has to
@@ -618,7 +810,8 @@ extern "C" int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, 
                                          int64_t capacity) {
   if (!L) return set_error(CGS_ERR_INVALID, "null layer");
   ConvGemmParams p;
-  int rc = backward ? make_backward_params(*L, B, nullptr, nullptr, p) : make_forward_params(*L, B, nullptr, nullptr, p);
+  int rc = use_scatter(*L, backward != 0) ? make_scatter_gemm_params(*L, backward != 0, B, nullptr, nullptr, p)
+           : backward ? make_backward_params(*L, B, nullptr, nullptr, p) : make_forward_params(*L, B, nullptr, nullptr, p);
   if (rc) return rc;
   const int64_t need = 14 + (int64_t)p.nclasses * (5 + 2 * kMaxTaps);
   if (!out) return need;

@@ -30,7 +30,7 @@ from cgs import runtime as R
 
 
 class Refiner():
-    def __init__(self, rollout_steps, rollout_rate, rollout_method="momentum", math="tf32"):
+    def __init__(self, rollout_steps, rollout_rate, rollout_method="momentum", math=None):
         self.forward_steps = rollout_steps
         self.optimizer = PolicyAdaptive(rollout_rate, rollout_method)
         self.log = False
@@ -57,6 +57,10 @@ class Refiner():
         self._g = spec_g.gtail
         self._spec = spec_g
         self._cimg = spec_g.image_shape[2]
+        if self.math is None:
+            self.math = spec_g.math
+        if spec_g.math != spec_d.math or self.math != spec_g.math:
+            raise ValueError("math mode of the refiner and of both specs must agree (weights are packed per mode)")
 
     def set_constraints(self, vmin, vmax):
         self.vmin = vmin

@@ -217,11 +217,24 @@ CGS_API int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* ky,
 CGS_API int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
                                       int64_t capacity);
 
-/* Single-layer entry points used by the per-layer parity tests.  x [B,hin,win,cs_in], y [B,hout,wout,cs_out]. */
-CGS_API int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y, cgs_stream_t stream);
-/* dx = dgrad(dy) * act'(x_prev_out) where prev_act describes the producer of x (CGS_ACT_NONE for none) */
+/* Lowering of a pass: 0 = gather layout (K order given by cgs_pack_map), 1 = scatter layout.  Transposed-type
+ * passes with <= 4 output channels (deconv -> image forward, first-conv data-gradient) run as one GEMM over the
+ * input pixels producing all k*k taps, followed by a col2im kernel with the fused epilogue; their packed matrix
+ * has rows = (ky*k + kx)*4 + small_channel and K = the large channel count.  Host only. */
+CGS_API int cgs_pass_layout(const cgs_layer_desc* L, int backward);
+
+/* Single-layer entry points used by the per-layer parity tests.  x [B,hin,win,cs_in], y [B,hout,wout,cs_out];
+ * workspace (cgs_layer_workspace_bytes) is only touched by scatter-lowered passes. */
+CGS_API size_t cgs_layer_workspace_bytes(const cgs_layer_desc* L, int64_t B);
+CGS_API int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y, void* workspace,
+                              size_t workspace_bytes, cgs_stream_t stream);
+/* dx = dgrad(dy) * act'(x_fwd) where prev_act describes the producer of x (CGS_ACT_NONE for none) */
 CGS_API int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, const float* dy, float* dx,
-                       const float* x_fwd, int prev_act, cgs_stream_t stream);
+                               const float* x_fwd, int prev_act, void* workspace, size_t workspace_bytes,
+                               cgs_stream_t stream);
+
+/* Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when env CGS_DEBUG has bit 256 set. */
+CGS_API int cgs_debug_trace(unsigned long long* out_host, int capacity);
 
 #ifdef __cplusplus
 }

@@ -58,3 +58,47 @@ def replay(p, x, w, B):
         R = A @ Wc.T                                         # [B, MH, MW, nvalid]
         out[:, g["oy0"]::p["os"], g["ox0"]::p["os"], :nvalid][:, :p["MH"], :p["MW"]] = R
     return out
+
+
+def pass_layout(layer, backward):
+    return L.load().cgs_pass_layout(C.byref(N._layer_desc(layer)), int(backward))
+
+
+def same_pad_before(size, k):
+    out = (size + 1) // 2
+    return max((out - 1) * 2 + k - size, 0) // 2
+
+
+def col2im(col, layer, backward, B):
+    """CPU twin of col2im_kernel: col [B, IH, IW, k*k*4] -> raw accumulators [B, OH, OW, 4]."""
+    k = layer["k"]
+    if not backward:     # deconv forward
+        IH, IW = layer["hin"], layer["win"]
+        OH, OW = IH * 2, IW * 2
+    else:                # conv data-gradient
+        OH, OW = layer["hin"], layer["win"]
+        IH, IW = (OH + 1) // 2, (OW + 1) // 2
+    py, px = same_pad_before(OH, k), same_pad_before(OW, k)
+    col = np.asarray(col, np.float64).reshape(B, IH, IW, k * k * 4)
+    out = np.zeros((B, OH, OW, 4))
+    for y in range(OH):
+        for ky in range(k):
+            ty = y + py - ky
+            if ty < 0 or ty % 2 or ty // 2 >= IH:
+                continue
+            for x in range(OW):
+                for kx in range(k):
+                    tx = x + px - kx
+                    if tx < 0 or tx % 2 or tx // 2 >= IW:
+                        continue
+                    out[:, y, x, :] += col[:, ty // 2, tx // 2, (ky * k + kx) * 4:(ky * k + kx) * 4 + 4]
+    return out
+
+
+def layer_pass(layer, backward, B, x_padded, w_packed):
+    """Raw accumulators of one pass, replayed on the CPU whichever lowering the library picks."""
+    p = gemm_params(layer, backward, B)
+    if pass_layout(layer, backward) == 1:
+        col = replay(p, np.asarray(x_padded, np.float64).reshape(p["M"], 1, 1, p["Cs"]), w_packed, p["M"])
+        return col2im(col.reshape(p["M"], p["ON"]), layer, backward, B)
+    return replay(p, x_padded, w_packed, B)

@@ -36,7 +36,7 @@ def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
     from cgs import nets as N
     arch = N.get_arch(arch_name)
     w = onets.init_weights(arch, seed=11)
-    spec = N.NetSpec(arch, w, cuda_device)
+    spec = N.NetSpec(arch, w, cuda_device, math=math)
     rng = np.random.RandomState(1)
     chain = [("generator", l, spec.gtail.layer_desc(i)) for i, l in enumerate(arch["gtail"])] + \
             [("discriminator", l, spec.d.layer_desc(i)) for i, l in enumerate(arch["d"][:-1])]
@@ -54,7 +54,9 @@ def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
         cs_in, cs_out = N.cstride(cin), N.cstride(cout)
         x_dev = torch.from_numpy(pad_c(x, cs_in)).to(cuda_device)
         y_dev = torch.full(tuple(y.shape[:-1]) + (cs_out,), float("nan"), device=cuda_device)
-        L.check(cgs_lib.cgs_layer_forward(C.byref(desc), L.MATH_IDS[math], B, L.ptr(x_dev), L.ptr(y_dev), L.stream_ptr()))
+        ws = torch.empty(int(cgs_lib.cgs_layer_workspace_bytes(C.byref(desc), B)), dtype=torch.uint8, device=cuda_device)
+        L.check(cgs_lib.cgs_layer_forward(C.byref(desc), L.MATH_IDS[math], B, L.ptr(x_dev), L.ptr(y_dev), L.ptr(ws),
+                                          ws.numel(), L.stream_ptr()))
         torch.cuda.synchronize()
         got = y_dev.cpu().numpy()
         e = rel_l2(got[..., :cout], y.detach().numpy())
@@ -64,7 +66,7 @@ def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
         dy_dev = torch.from_numpy(pad_c(dy, cs_out)).to(cuda_device)
         dx_dev = torch.full(tuple(x.shape[:-1]) + (cs_in,), float("nan"), device=cuda_device)
         L.check(cgs_lib.cgs_layer_backward(C.byref(desc), L.MATH_IDS[math], B, L.ptr(dy_dev), L.ptr(dx_dev), None, 0,
-                                           L.stream_ptr()))
+                                           L.ptr(ws), ws.numel(), L.stream_ptr()))
         torch.cuda.synchronize()
         gotg = dx_dev.cpu().numpy()
         e = rel_l2(gotg[..., :cin], dx.numpy())
@@ -73,11 +75,11 @@ def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
     print(arch_name, math, {k: "%.2e" % v for k, v in worst.items()})
 
 
-def _make(arch_name, seed, gain, cuda_device):
+def _make(arch_name, seed, gain, cuda_device, math="fp32"):
     from cgs import nets as N
     arch = N.get_arch(arch_name)
     w = onets.scale_weights_for_signal(arch, onets.init_weights(arch, seed=seed), gain)
-    return arch, w, N.NetSpec(arch, w, cuda_device)
+    return arch, w, N.NetSpec(arch, w, cuda_device, math=math)
 
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
@@ -85,10 +87,10 @@ def _make(arch_name, seed, gain, cuda_device):
 def test_forward_logits_and_grad(cgs_lib, cuda_device, arch_name, B, gain, math):
     from cgs import nets as N
     from sampling.collaborator import Refiner
-    arch, w, spec = _make(arch_name, 5, gain, cuda_device)
+    arch, w, spec = _make(arch_name, 5, gain, cuda_device, math)
     h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(1)))
     logit_ref, grad_ref, img_ref = gr.forward_logits_and_grad(h0, arch, w)
-    ref = Refiner(1, 0.1, math=math)
+    ref = Refiner(1, 0.1)
     ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     logit, grad = ref.compute_forward_logits_and_grad(h0.to(cuda_device))
     img, logit2 = ref.feature_to_image(h0.to(cuda_device))
@@ -110,10 +112,10 @@ def test_forward_logits_and_grad(cgs_lib, cuda_device, arch_name, B, gain, math)
 def test_build_refiner_matches_oracle(cgs_lib, cuda_device, arch_name, B, K, method, gain, math):
     from cgs import nets as N
     from sampling.collaborator import Refiner
-    arch, w, spec = _make(arch_name, 9, gain, cuda_device)
+    arch, w, spec = _make(arch_name, 9, gain, cuda_device, math)
     h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(2)))
     o = gr.build_refiner(h0, arch, w, K, 0.1, method=method)
-    ref = Refiner(K, 0.1, method, math=math)
+    ref = Refiner(K, 0.1, method)
     ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     out = ref.build_refiner(h0.to(cuda_device), None, "deterministic", keep_optimal_feature=True)
     tol = 1e-4 if math == "fp32" else 5e-2
@@ -138,13 +140,13 @@ def test_probabilistic_mode_and_clip(cgs_lib, cuda_device):
     h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(3)))
     idx = np.array([0, 1, 2, 3, 4, 4, 0])        # value K keeps the proposal (collaborator.py:77,81-83)
     o = gr.build_refiner(h0, arch, w, K, 0.1, mode="probabilistic", prob_indices=idx)
-    ref = Refiner(K, 0.1, math="fp32")
+    ref = Refiner(K, 0.1)
     ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     out = ref.build_refiner(h0.to(cuda_device), None, "probabilistic", prob_indices=idx)
     assert rel_l2(out.cpu().numpy(), o["refined"].numpy()) <= 1e-4
     assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
     # clipping (collaborator.py:69-70); a zero bound disables it (truthiness test, sic)
-    ref2 = Refiner(K, 0.1, math="fp32")
+    ref2 = Refiner(K, 0.1)
     ref2.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     ref2.set_constraints(0.05, 0.8)
     o2 = gr.build_refiner(h0, arch, w, K, 0.1, vmin=0.05, vmax=0.8)

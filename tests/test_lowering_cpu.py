@@ -43,19 +43,19 @@ def test_layer_forward_and_dgrad_lowering(cgs_lib, arch_name):
             dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
             (dx,) = torch.autograd.grad((y * dy).sum(), xt)
             # replay forward
-            pf = emulate.gemm_params(layer, False, B)
-            cs_in = pf["Cs"]
-            xp = np.zeros((B, pf["IH"], pf["IW"], cs_in))
-            xp[..., :cin] = x.reshape(B, pf["IH"], pf["IW"], cin)
-            acc = emulate.replay(pf, xp, w_fwd.numpy(), B)
+            cs_in, cs_out = N.cstride(cin), N.cstride(cout)
+            hin, win = (layer["hin"], layer["win"]) if layer["type"] != "fc" else (1, 1)
+            xp = np.zeros((B, hin, win, cs_in))
+            xp[..., :cin] = x.reshape(B, hin, win, cin)
+            acc = emulate.layer_pass(layer, False, B, xp, w_fwd.numpy())
             got = acc[..., :cout] + bias.numpy()[:cout]
             ref = y.detach().numpy().reshape(got.shape)
             assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), (layer["name"], "fwd")
             assert np.all(acc[..., cout:] == 0)
             # replay backward
-            pb = emulate.gemm_params(layer, True, B)
-            dyp = np.zeros((B, pb["IH"], pb["IW"], pb["Cs"]))
-            dyp[..., :cout] = dy.numpy().reshape(B, pb["IH"], pb["IW"], cout)
-            gacc = emulate.replay(pb, dyp, w_bwd.numpy(), B)
-            gref = dx.numpy().reshape(B, pb["OH"], pb["OW"], cin)
+            hout, wout = (y.shape[1], y.shape[2]) if layer["type"] != "fc" else (1, 1)
+            dyp = np.zeros((B, hout, wout, cs_out))
+            dyp[..., :cout] = dy.numpy().reshape(B, hout, wout, cout)
+            gacc = emulate.layer_pass(layer, True, B, dyp, w_bwd.numpy())
+            gref = dx.numpy().reshape(B, hin, win, cin)
             assert np.abs(gacc[..., :cin] - gref).max() <= 1e-4 * max(1.0, np.abs(gref).max()), (layer["name"], "bwd")

@@ -1,0 +1,54 @@
+"""Run one layer pass with the CTA-0 pipeline trace on (CGS_DEBUG |= 256) and print per-role event timelines."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+os.environ["CGS_DEBUG"] = str(int(os.environ.get("CGS_DEBUG", "0")) | 256)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "collaborative-gan-sampling_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from cgs import lib as L, nets as N, synthetic as S  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="mnist")
+ap.add_argument("--layer", default="d_conv2")
+ap.add_argument("--bwd", action="store_true")
+ap.add_argument("--batch", type=int, default=1024)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+lib = L.load()
+arch = N.get_arch(a.workload)
+spec = N.NetSpec(arch, S.init_weights(arch, gain=2.5), dev)
+chain = [(l, spec.gtail.layer_desc(i)) for i, l in enumerate(arch["gtail"])] + \
+        [(l, spec.d.layer_desc(i)) for i, l in enumerate(arch["d"][:-1])]
+layer, desc = [c for c in chain if c[0]["name"] == a.layer][0]
+B = a.batch
+cin, cout = layer["cin"], layer["cout"]
+if layer["type"] == "fc":
+    xs, ys = (B, cin), (B, N.cstride(cout))
+elif layer["type"] == "conv":
+    xs = (B, layer["hin"], layer["win"], N.cstride(cin)); ys = (B, (layer["hin"] + 1) // 2, (layer["win"] + 1) // 2, N.cstride(cout))
+else:
+    xs = (B, layer["hin"], layer["win"], N.cstride(cin)); ys = (B, layer["hin"] * 2, layer["win"] * 2, N.cstride(cout))
+x = torch.randn(xs, device=dev); y = torch.empty(ys, device=dev); dy = torch.randn(ys, device=dev); dx = torch.empty(xs, device=dev)
+buf = np.zeros(16384, np.uint64)
+ws = torch.empty(int(lib.cgs_layer_workspace_bytes(C.byref(desc), B)), dtype=torch.uint8, device=dev)
+for rep in range(2):
+    if a.bwd:
+        L.check(lib.cgs_layer_backward(C.byref(desc), 0, B, L.ptr(dy), L.ptr(dx), L.ptr(x), 1, L.ptr(ws), ws.numel(), L.stream_ptr()))
+    else:
+        L.check(lib.cgs_layer_forward(C.byref(desc), 0, B, L.ptr(x), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    n = lib.cgs_debug_trace(buf.ctypes.data, 16384)
+ev = [(int(v >> 60), int((v >> 56) & 0xf), int((v >> 32) & 0xffffff), int(v & 0xffffffff)) for v in buf[:n].tolist() if v]
+t0 = min(e[3] for e in ev)
+names = {(0, 0): "P.wait_empty", (0, 1): "P.issued", (1, 0): "T.wait_empty", (2, 0): "M.wait_full", (2, 1): "M.commit",
+         (2, 2): "M.tmem_empty", (3, 0): "E.tmem_full", (3, 1): "E.released", (3, 2): "E.done"}
+print("events", len(ev))
+for key in sorted(names):
+    rows = sorted([(e[2], (e[3] - t0) & 0xffffffff) for e in ev if (e[0], e[1]) == key])
+    ts = [t for _, t in rows]
+    d = np.diff(ts) if len(ts) > 1 else []
+    print("%-14s n=%4d first=%7d last=%8d  mean dt=%7.1f  first 40 t: %s" % (names[key], len(ts), ts[0] if ts else -1, ts[-1] if ts else -1,
+          float(np.mean(d)) if len(d) else 0.0, ts[:40]))
