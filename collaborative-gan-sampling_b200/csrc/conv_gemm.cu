@@ -17,6 +17,7 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace cgs {
 
@@ -43,8 +44,10 @@ constexpr int kTmaWarp = kMmaWarp + 1;                 // 13
 constexpr int kThreads = (kTmaWarp + 1) * 32;          // 448
 constexpr int kRowsPerThread = BM / (kProdWarps * 4);  // 4
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
-constexpr int EPI_PITCH = 36;                // floats per staged row (16-byte aligned, conflict-free for LDS/STS.128)
-constexpr int EPI_STAGE_BYTES = kEpiWarps * 32 * EPI_PITCH * 4;   // 18 KB
+constexpr int EPI_CH = 16;                   // accumulator columns per TMEM load / staging pass
+constexpr int EPI_PITCH = 20;                // floats per staged row (16-byte aligned; STS.128 by row is conflict-free)
+constexpr int kMaxEpiWarps = kEpiWarps + kProdWarps;              // producer warps help in TMA mode
+constexpr int EPI_STAGE_BYTES = kMaxEpiWarps * 32 * EPI_PITCH * 4;   // 30 KB
 
 template <int BN>
 struct Cfg {
@@ -57,7 +60,8 @@ struct Cfg {
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_a) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
@@ -77,17 +81,21 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], (p.debug & 128) ? kProdWarps + 1 : kProdWarps * 32 + 1);   // async arrive of every producer thread + the TMA thread
+      // TMA mode: the TMA thread's arrive.expect_tx only; gather mode: + the async arrive of every producer thread
+      mbar_init(&full_bar[s], p.a_tma ? 1 : kProdWarps * 32 + 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], p.a_tma ? kMaxEpiWarps : kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    if (p.a_tma) tma_prefetch_desc(&tmap_a);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -95,10 +103,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   const int tiles_per_class = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_per_class * p.nclasses;
-  const int per_img = p.MH * p.MW;
+  const int rows_per_img_tile = p.BH * p.MW;   // rows one image contributes to a tile
 
-  if (warp >= kEpiWarps && warp < kMmaWarp) {
-    // ------------------------------------------------------------------ A producers
+  if (warp >= kEpiWarps && warp < kMmaWarp && !p.a_tma) {
+    // ------------------------------------------------------------------ A producers (gather mode only)
+    {
     const int pw = warp - kEpiWarps;
     const int chunk = lane & 7;           // 16-byte chunk inside the 128-byte row
     const int rsub = lane >> 3;           // 0..3
@@ -123,14 +132,15 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 #pragma unroll
       for (int it = 0; it < kRowsPerThread; ++it) {
         const int r = pw * (4 * kRowsPerThread) + it * 4 + rsub;
-        const int m = m_tile * BM + r;
         rbase[it] = 0;
         vmask[it] = 0;
-        if (m < p.M) {
-          const int b = m / per_img;
-          const int q = m - b * per_img;
-          const int j = q / p.MW;
-          const int i = q - j * p.MW;
+        const int bb = r / rows_per_img_tile;
+        const int q = r - bb * rows_per_img_tile;
+        const int hh = q / p.MW;
+        const int i = q - hh * p.MW;
+        const int b = (m_tile / p.hy_tiles) * p.BB + bb;
+        const int j = (m_tile % p.hy_tiles) * p.BH + hh;
+        if (r < p.rows_valid && b < p.B && j < p.MH) {
           const int y0 = j * p.S, x0 = i * p.S;
           rbase[it] = ((b * p.IH + y0) * p.IW + x0) * p.Cs;
           uint32_t mx = 0;
@@ -179,17 +189,25 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         }
       }
     }
+    }  // !a_tma
   } else if (warp == kTmaWarp) {
-    // ------------------------------------------------------------------ TMA producer (weights)
+    // ------------------------------------------------------------------ TMA producer (weights, and A tiles in TMA mode)
     // whole warp walks the loop (uniform control flow); one elected lane issues
     const uint32_t smem_b_u32 = smem_u32(smem_b);
+    const uint32_t smem_a_u32 = smem_u32(smem_a);
     uint32_t it_global = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ci = tile / tiles_per_class;
       const int rem = tile - ci * tiles_per_class;
+      const int m_tile = rem / p.n_tiles;
       const int n_tile = rem % p.n_tiles;
-      const int k0 = p.cls[ci].k0;
-      const int nkb = p.cls[ci].nkb;
+      const GemmClass& gc = p.cls[ci];
+      const int k0 = gc.k0;
+      const int nkb = gc.nkb;
+      const int b0 = (m_tile / p.hy_tiles) * p.BB;
+      const int y_tile = (m_tile % p.hy_tiles) * p.BH * p.S;
+      const uint32_t a_bytes = p.a_tma ? (uint32_t)p.rows_valid * 128u : 0u;
+      int t = 0, cb = 0;
       for (int kb = 0; kb < nkb; ++kb, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
@@ -199,11 +217,17 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           if (p.debug & 2) {
             mbar_arrive(&full_bar[s]);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES + a_bytes);
             tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], k0 + kb * BK, n_tile * BN);
+            if (p.a_tma)   // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
+              tma_load_4d(smem_a_u32 + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, gc.dx[t], y_tile + gc.dy[t], b0);
           }
         }
         __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++t;
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -230,7 +254,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         if (elect_one()) {
           trace(p, 2, 0, it_global);
           // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-          if (!(p.debug & 64)) fence_proxy_async_smem();
+          if (!p.a_tma) fence_proxy_async_smem();
           // descriptor address field is in 16-byte units: + stage offset, + 32 bytes per K=8 step
           const uint64_t da = da0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
           const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
@@ -247,10 +271,15 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-3)
-    constexpr int CH = BN >= 32 ? 32 : 16;         // accumulator columns per TMEM load
-    constexpr int Q = CH / 4;                      // float4 per staged row
+    // ------------------------------------------------------------------ epilogue
+    // warps 0-3 always; in TMA mode the 8 idle producer warps join.  A warp may only touch the TMEM lane quarter
+    // (warp % 4), so the warps of one quarter split the accumulator columns in 16-column chunks.
+    constexpr int Q = EPI_CH / 4;                  // float4 per staged row
     constexpr int ROWS_PER_PASS = 32 / Q;          // rows covered by one warp-wide 16-byte access
+    constexpr int PASSES = 32 / ROWS_PER_PASS;
+    const int quarter = warp & 3;
+    const int group = warp >> 2;                   // 0..2
+    const int ngroups = p.a_tma ? kMaxEpiWarps / 4 : 1;
     float* stage = smem_epi + warp * 32 * EPI_PITCH;
     const int c4 = lane % Q;
     const int rsub = lane / Q;
@@ -263,26 +292,42 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const GemmClass& gc = p.cls[ci];
       const uint32_t acc = tile_count & 1;
       const uint32_t acc_ph = (tile_count >> 1) & 1;
-      const int m = m_tile * BM + warp * 32 + lane;
       int row_off = -1;                            // element offset of this lane's row in out / aux / mom
-      if (m < p.M) {
-        const int b = m / per_img;
-        const int q = m - b * per_img;
-        const int j = q / p.MW;
-        const int i = q - j * p.MW;
-        row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
+      {
+        const int r = quarter * 32 + lane;
+        const int bb = r / rows_per_img_tile;
+        const int q = r - bb * rows_per_img_tile;
+        const int hh = q / p.MW;
+        const int i = q - hh * p.MW;
+        const int b = (m_tile / p.hy_tiles) * p.BB + bb;
+        const int j = (m_tile % p.hy_tiles) * p.BH + hh;
+        if (r < p.rows_valid && b < p.B && j < p.MH)
+          row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
       }
+      int ro[PASSES];                              // row offsets of the rows this lane stores
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) ro[ps] = __shfl_sync(0xffffffffu, row_off, ps * ROWS_PER_PASS + rsub);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      // last chunk index owned by this warp (it releases the accumulator after loading it)
+      constexpr int NCH = BN / EPI_CH;
+      int last_own = -1;
+      for (int ch = group; ch < NCH; ch += ngroups) last_own = ch;
+      if (last_own < 0) {                          // nothing to do for this warp on such narrow tiles
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        uint32_t v[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, v); else tmem_ld_32x32b_x16(taddr + c0, v);
+      for (int ch = group; ch < NCH; ch += ngroups) {
+        const int c0 = ch * EPI_CH;
+        uint32_t v[EPI_CH];
+        tmem_ld_32x32b_x16(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 + CH >= BN) {
-          // all TMEM reads of this accumulator are done: hand it back before the global-memory part
+        if (ch == last_own) {
+          // all TMEM reads of this warp for this accumulator are done: hand it back before the global-memory part
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -290,7 +335,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         }
         const int nbase = n_tile * BN + c0;
         if (nbase >= p.ON || (p.debug & 16)) continue;        // warp-uniform
-        // lane = row: stage 32 rows x CH columns, then re-read with lane = (row group, 16-byte column)
+        // lane = row: stage 32 rows x 16 columns, then re-read with lane = (row group, 16-byte column)
 #pragma unroll
         for (int q4 = 0; q4 < Q; ++q4)
           *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + q4 * 4) =
@@ -298,13 +343,30 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
                           __uint_as_float(v[4 * q4 + 3]));
         __syncwarp();
         const int n = nbase + c4 * 4;
+        const bool n_ok = n < p.ON;                // ON is a multiple of 4
+        // issue every global read of the pass set first (independent loads in flight), then compute + store
+        float4 x0[PASSES], x1[PASSES];
+        if (p.epi == EPI_BWD) {
 #pragma unroll
-        for (int rp = 0; rp < 32; rp += ROWS_PER_PASS) {
-          const int rr = rp + rsub;
-          const int ro = __shfl_sync(0xffffffffu, row_off, rr);
-          if (ro >= 0 && n < p.ON) {               // ON is a multiple of 4
+          for (int ps = 0; ps < PASSES; ++ps)
+            if (ro[ps] >= 0 && n_ok) x0[ps] = __ldg(reinterpret_cast<const float4*>(p.aux + ro[ps] + n));
+        } else if (p.epi == EPI_UPDATE) {
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps)
+            if (ro[ps] >= 0 && n_ok) {
+              x0[ps] = *reinterpret_cast<const float4*>(p.out + ro[ps] + n);
+              if (!p.sgd && !p.first) x1[ps] = *reinterpret_cast<const float4*>(p.mom + ro[ps] + n);
+            }
+        } else if (p.epi == EPI_FWD) {
+          x0[0] = (p.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          if (ro[ps] >= 0 && n_ok) {
+            const int rr = ps * ROWS_PER_PASS + rsub;
             const float4 a = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + c4 * 4);
-            *reinterpret_cast<float4*>(p.out + ro + n) = epilogue4(p, ro + n, n, a);
+            const float4 o = epilogue4(p, ro[ps] + n, a, p.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
+            *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o;
           }
         }
         __syncwarp();
@@ -355,8 +417,15 @@ conv_gemm_simt_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
       }
     }
     const int row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
-    *reinterpret_cast<float4*>(p.out + row_off + ng * 4) =
-        epilogue4(p, row_off + ng * 4, ng * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    const int off = row_off + ng * 4;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (p.epi == EPI_FWD) { if (p.bias) x0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng * 4)); }
+    else if (p.epi == EPI_BWD) x0 = __ldg(reinterpret_cast<const float4*>(p.aux + off));
+    else if (p.epi == EPI_UPDATE) {
+      x0 = *reinterpret_cast<const float4*>(p.out + off);
+      if (!p.sgd && !p.first) x1 = *reinterpret_cast<const float4*>(p.mom + off);
+    }
+    *reinterpret_cast<float4*>(p.out + off) = epilogue4(p, off, make_float4(acc[0], acc[1], acc[2], acc[3]), x0, x1);
   }
 }
 
@@ -408,7 +477,36 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
     p.debug = dbg;
   }
   p.n_tiles = (p.N + BN - 1) / BN;
-  p.m_tiles = (p.M + BM - 1) / BM;
+  // tile geometry: BB images x BH rows x MW columns (<= 128 rows) per row tile
+  const int per_img = p.MH * p.MW;
+  if (p.MW > BM) return set_error(CGS_ERR_UNSUPPORTED, "row width %d of the output grid exceeds the 128-row tile", p.MW);
+  p.B = p.M / per_img;
+  if (per_img >= BM) {
+    p.BB = 1;
+    p.BH = BM / p.MW;
+  } else {
+    p.BH = p.MH;
+    p.BB = BM / per_img;
+  }
+  p.hy_tiles = (p.MH + p.BH - 1) / p.BH;
+  p.rows_valid = p.BB * p.BH * p.MW;
+  p.m_tiles = ((p.B + p.BB - 1) / p.BB) * p.hy_tiles;
+  p.a_tma = (p.cblocks > 0) && !(p.debug & 512);
+  CUtensorMap tmap_a;
+  std::memset(&tmap_a, 0, sizeof(tmap_a));
+  if (p.a_tma) {
+    // input viewed as [B][IH][IW][Cs]; traversal strides S pick every S-th pixel, so a box of
+    // {32 ch, MW*S, BH*S, BB} lands as BB*BH*MW rows of 128 bytes; out-of-range coordinates read zeros
+    if (p.MW * p.S > 256 || p.BH * p.S > 256) return set_error(CGS_ERR_UNSUPPORTED, "TMA box too large");
+    cuuint64_t adim[4] = {(cuuint64_t)p.Cs, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.B};
+    cuuint64_t astr[3] = {(cuuint64_t)p.Cs * 4, (cuuint64_t)p.IW * p.Cs * 4, (cuuint64_t)p.IH * p.IW * p.Cs * 4};
+    cuuint32_t abox[4] = {(cuuint32_t)BK, (cuuint32_t)(p.MW * p.S), (cuuint32_t)(p.BH * p.S), (cuuint32_t)p.BB};
+    cuuint32_t aest[4] = {1, (cuuint32_t)p.S, (cuuint32_t)p.S, 1};
+    CUresult ra = enc(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), adim, astr, abox, aest,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ra != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (A operand) failed (%d)", (int)ra);
+  }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -424,7 +522,7 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   }
   const int total = p.m_tiles * p.n_tiles * p.nclasses;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap); count_launch();
+  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap, tmap_a); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;

@@ -50,7 +50,11 @@ struct ConvGemmParams {
   int OH, OW, ON, os; // output image, channel stride, output pixel stride
   int N;              // valid output channels
   int n_tiles;        // ceil(N / BLOCK_N)
-  int m_tiles;        // ceil(M / 128)
+  int m_tiles;        // row tiles (see tile geometry)
+  // tile geometry (filled by the launcher): a row tile = BB images x BH rows x MW columns of the M-space
+  // (<= 128 rows, row r = (bb*BH + hh)*MW + ww), so that the A operand of a K block is ONE TMA box
+  int B, BH, BB, hy_tiles, rows_valid;
+  int a_tma;          // 1: A tiles fetched by TMA (channel-block mode); 0: cp.async gather (pixel mode)
   int nclasses;
   int epi, act;
   int first, clip, sgd;
@@ -84,37 +88,35 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
-// Four consecutive output channels.  `off` = element offset of (row, n) in out / aux / mom (multiple of 4).
-__device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, int n, float4 a) {
+// Four consecutive output channels.  `off` = element offset in mom; x0 / x1 are the operands the caller has already
+// fetched (so that many loads can be in flight): FWD x0 = bias; BWD x0 = forward output of the differentiated layer;
+// UPDATE x0 = current feature, x1 = momentum.
+__device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, float4 a, float4 x0, float4 x1) {
   float4 o = a;
   if (p.epi == EPI_FWD) {
-    const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    o.x = act_apply(a.x + b.x, p.act);
-    o.y = act_apply(a.y + b.y, p.act);
-    o.z = act_apply(a.z + b.z, p.act);
-    o.w = act_apply(a.w + b.w, p.act);
+    o.x = act_apply(a.x + x0.x, p.act);
+    o.y = act_apply(a.y + x0.y, p.act);
+    o.z = act_apply(a.z + x0.z, p.act);
+    o.w = act_apply(a.w + x0.w, p.act);
   } else if (p.epi == EPI_BWD) {
-    const float4 y = __ldg(reinterpret_cast<const float4*>(p.aux + off));
-    o.x = a.x * act_grad_from_output(y.x, p.act);
-    o.y = a.y * act_grad_from_output(y.y, p.act);
-    o.z = a.z * act_grad_from_output(y.z, p.act);
-    o.w = a.w * act_grad_from_output(y.w, p.act);
+    o.x = a.x * act_grad_from_output(x0.x, p.act);
+    o.y = a.y * act_grad_from_output(x0.y, p.act);
+    o.z = a.z * act_grad_from_output(x0.z, p.act);
+    o.w = a.w * act_grad_from_output(x0.w, p.act);
   } else if (p.epi == EPI_UPDATE) {
     // sampling/policy.py:27-37; separately rounded multiplies / adds like the reference's un-fused TF ops
     float4 m;
     m.x = __fmul_rn(p.rate, a.x); m.y = __fmul_rn(p.rate, a.y); m.z = __fmul_rn(p.rate, a.z); m.w = __fmul_rn(p.rate, a.w);
     if (!p.sgd) {
       if (!p.first) {
-        const float4 mo = *reinterpret_cast<const float4*>(p.mom + off);
-        m.x = __fadd_rn(__fmul_rn(p.alpha, mo.x), m.x);
-        m.y = __fadd_rn(__fmul_rn(p.alpha, mo.y), m.y);
-        m.z = __fadd_rn(__fmul_rn(p.alpha, mo.z), m.z);
-        m.w = __fadd_rn(__fmul_rn(p.alpha, mo.w), m.w);
+        m.x = __fadd_rn(__fmul_rn(p.alpha, x1.x), m.x);
+        m.y = __fadd_rn(__fmul_rn(p.alpha, x1.y), m.y);
+        m.z = __fadd_rn(__fmul_rn(p.alpha, x1.z), m.z);
+        m.w = __fadd_rn(__fmul_rn(p.alpha, x1.w), m.w);
       }
       *reinterpret_cast<float4*>(p.mom + off) = m;
     }
-    const float4 h = *reinterpret_cast<const float4*>(p.out + off);
-    o.x = __fsub_rn(h.x, m.x); o.y = __fsub_rn(h.y, m.y); o.z = __fsub_rn(h.z, m.z); o.w = __fsub_rn(h.w, m.w);
+    o.x = __fsub_rn(x0.x, m.x); o.y = __fsub_rn(x0.y, m.y); o.z = __fsub_rn(x0.z, m.z); o.w = __fsub_rn(x0.w, m.w);
     if (p.clip) {                                                    // collaborator.py:69-70
       o.x = fminf(fmaxf(o.x, p.vmin), p.vmax); o.y = fminf(fmaxf(o.y, p.vmin), p.vmax);
       o.z = fminf(fmaxf(o.z, p.vmin), p.vmax); o.w = fminf(fmaxf(o.w, p.vmin), p.vmax);
