@@ -43,7 +43,7 @@ constexpr int kMmaWarp = kEpiWarps + kProdWarps;       // 12
 constexpr int kTmaWarp = kMmaWarp + 1;                 // 13
 constexpr int kThreads = (kTmaWarp + 1) * 32;          // 448
 constexpr int kRowsPerThread = BM / (kProdWarps * 4);  // 4
-constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int A_ATOM_BYTES = BM * BK * 4;    // 16 KB: 128 rows x one 128-byte swizzle row
 constexpr int EPI_CH = 16;                   // accumulator columns per TMEM load / staging pass
 constexpr int EPI_PITCH = 20;                // floats per staged row (16-byte aligned; STS.128 by row is conflict-free)
 constexpr int kMaxEpiWarps = kEpiWarps + kProdWarps;              // producer warps help in TMA mode
@@ -51,9 +51,14 @@ constexpr int EPI_STAGE_BYTES = kMaxEpiWarps * 32 * EPI_PITCH * 4;   // 30 KB
 
 template <int BN>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 4;
+  // K blocks ("atoms" of 32 floats) per pipeline stage: the per-stage barrier handshakes of the single-thread TMA and
+  // MMA roles cost ~400 cycles, so narrow tiles (short MMAs) take two atoms per stage to amortise them
+  static constexpr int KB = (BN >= 256) ? 1 : 2;
+  static constexpr int B_ATOM_BYTES = BN * BK * 4;
+  static constexpr int A_STAGE_BYTES = KB * A_ATOM_BYTES;
+  static constexpr int B_STAGE_BYTES = KB * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -67,7 +72,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
+  uint8_t* smem_b = smem + C::STAGES * C::A_STAGE_BYTES;
   float* smem_epi = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;
@@ -154,39 +159,42 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       }
       int t = 0, cb = 0;                  // block mode: current tap / channel block
       int tap_off = pixel_mode ? 0 : (gc.dy[0] * p.IW + gc.dx[0]) * p.Cs;
-      for (int kb = 0; kb < gc.nkb; ++kb, ++it_global) {
+      for (int kb = 0; kb < gc.nkb; kb += C::KB, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
-        int off, tt;
-        if (pixel_mode) {
-          tt = kb * 8 + chunk;            // one tap (4 channels = 16 B) per chunk
-          const bool tap_ok = tt < gc.ntaps;
-          off = tap_ok ? (gc.dy[tt] * p.IW + gc.dx[tt]) * p.Cs : 0;
-          if (!tap_ok) tt = 31;           // bit 31 is never set (ntaps <= 25)
-        } else {
-          tt = t;
-          off = tap_off + cb * BK + chunk * 4;
-        }
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (pw == 0 && lane == 0) trace(p, 0, 0, it_global);
-        const uint32_t stage_base = smem_a_u32 + s * A_STAGE_BYTES;
-        if (!(p.debug & 1)) {
 #pragma unroll
-          for (int it = 0; it < kRowsPerThread; ++it) {
-            const bool ok = (vmask[it] >> tt) & 1u;
-            cp_async_16(stage_base + soff[it], p.in + (ok ? rbase[it] + off : 0), ok ? 16u : 0u);
+        for (int a = 0; a < C::KB; ++a) {
+          if (kb + a >= gc.nkb) break;
+          int off, tt;
+          if (pixel_mode) {
+            tt = (kb + a) * 8 + chunk;    // one tap (4 channels = 16 B) per chunk
+            const bool tap_ok = tt < gc.ntaps;
+            off = tap_ok ? (gc.dy[tt] * p.IW + gc.dx[tt]) * p.Cs : 0;
+            if (!tap_ok) tt = 31;         // bit 31 is never set (ntaps <= 25)
+          } else {
+            tt = t;
+            off = tap_off + cb * BK + chunk * 4;
+          }
+          const uint32_t atom_base = smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES;
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int it = 0; it < kRowsPerThread; ++it) {
+              const bool ok = (vmask[it] >> tt) & 1u;
+              cp_async_16(atom_base + soff[it], p.in + (ok ? rbase[it] + off : 0), ok ? 16u : 0u);
+            }
+          }
+          if (!pixel_mode && ++cb == p.cblocks) {
+            cb = 0;
+            ++t;
+            if (t < gc.ntaps) tap_off = (gc.dy[t] * p.IW + gc.dx[t]) * p.Cs;
           }
         }
         // the copies of this thread arrive on the stage's full barrier when they land: no wait on the issue side,
-        // so up to STAGES K blocks of gathers are in flight per CTA
-        if (p.debug & 128) { __syncwarp(); if (lane == 0) mbar_arrive(&full_bar[s]); } else
+        // so up to STAGES stages of gathers are in flight per CTA
         cp_async_mbar_arrive_noinc(&full_bar[s]);
         if (pw == 0 && lane == 0) trace(p, 0, 1, it_global);
-        if (!pixel_mode && ++cb == p.cblocks) {
-          cb = 0;
-          ++t;
-          if (t < gc.ntaps) tap_off = (gc.dy[t] * p.IW + gc.dx[t]) * p.Cs;
-        }
       }
     }
     }  // !a_tma
@@ -208,26 +216,39 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const int y_tile = (m_tile % p.hy_tiles) * p.BH * p.S;
       const uint32_t a_bytes = p.a_tma ? (uint32_t)p.rows_valid * 128u : 0u;
       int t = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++it_global) {
+      for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
+        const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           trace(p, 1, 0, it_global);
           if (p.debug & 2) {
             mbar_arrive(&full_bar[s]);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES + a_bytes);
-            tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], k0 + kb * BK, n_tile * BN);
-            if (p.a_tma)   // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
-              tma_load_4d(smem_a_u32 + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, gc.dx[t], y_tile + gc.dy[t], b0);
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * (C::B_ATOM_BYTES + a_bytes));
+            int tt = t, cc = cb;
+#pragma unroll
+            for (int a = 0; a < C::KB; ++a) {
+              if (a >= na) break;
+              tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES + a * C::B_ATOM_BYTES, &tmap_w, &full_bar[s],
+                          k0 + (kb + a) * BK, n_tile * BN);
+              if (p.a_tma)   // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
+                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s], cc * BK,
+                            gc.dx[tt], y_tile + gc.dy[tt], b0);
+              if (++cc == p.cblocks) {
+                cc = 0;
+                ++tt;
+              }
+            }
           }
         }
         __syncwarp();
-        if (++cb == p.cblocks) {
-          cb = 0;
-          ++t;
-        }
+        for (int a = 0; a < na; ++a)
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++t;
+          }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -246,25 +267,31 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < nkb; ++kb, ++it_global) {
+      for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
+        const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
           trace(p, 2, 0, it_global);
           // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           if (!p.a_tma) fence_proxy_async_smem();
-          // descriptor address field is in 16-byte units: + stage offset, + 32 bytes per K=8 step
-          const uint64_t da = da0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
+          // descriptor address field is in 16-byte units: + stage / atom offset, + 32 bytes per K=8 step
+          const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
           const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
           if (!(p.debug & 4)) {
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int a = 0; a < C::KB; ++a) {
+              if (a >= na) break;
+#pragma unroll
+              for (int k = 0; k < BK / 8; ++k)
+                umma_tf32_ss(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
+                             (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
-          if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete
+          if (kb + C::KB >= nkb) umma_commit(&tmem_full_bar[acc]);   // accumulator complete
           trace(p, 2, 1, it_global);
         }
         __syncwarp();
@@ -457,6 +484,24 @@ int pick_bn(int N) {
   return 256;
 }
 
+// Row tiles of a launch (same geometry rule as launch_tc).
+int count_m_tiles(const ConvGemmParams& p) {
+  const int per_img = p.MH * p.MW;
+  const int B = p.M / per_img;
+  int BH, BB;
+  if (per_img >= BM) { BB = 1; BH = BM / p.MW; } else { BH = p.MH; BB = BM / per_img; }
+  return ((B + BB - 1) / BB) * ((p.MH + BH - 1) / BH);
+}
+
+// Widest BN that still gives every SM a tile; narrow problems (e.g. fc 1024x1024 at batch 1024) trade tile width
+// for parallelism.  Depends on the layer shape and batch only through the tile COUNT, never on the data.
+int pick_bn_for(const ConvGemmParams& p, int num_sms) {
+  int bn = pick_bn(p.N);
+  const int mt = count_m_tiles(p) * p.nclasses;
+  while (bn > 64 && mt * ((p.N + bn - 1) / bn) < num_sms) bn >>= 1;
+  return bn;
+}
+
 template <int BN>
 int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -554,7 +599,13 @@ int debug_trace_read(unsigned long long* out, int cap) {
 int launch_conv_gemm_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   if (int rc = validate(p, w_cols)) return rc;
   if (p.M <= 0) return CGS_OK;
-  switch (pick_bn(p.N)) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  switch (pick_bn_for(p, num_sms)) {
     case 16: return launch_tc<16>(p, w, w_rows, w_cols, stream);
     case 32: return launch_tc<32>(p, w, w_rows, w_cols, stream);
     case 64: return launch_tc<64>(p, w, w_rows, w_cols, stream);
