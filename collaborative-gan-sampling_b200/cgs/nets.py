@@ -165,10 +165,20 @@ def pack_layer(layer, w, b):
         out[:, :, :small, :] = m
         return out.reshape(k * k * 4, big).contiguous()
 
+    def window():
+        """rows = large channel, K index = ky*32 + kx*4 + small channel (cgs_pass_layout == 2)."""
+        k = layer["k"]
+        small, big = w.shape[2], w.shape[3]                # conv [k,k,cin,cout] fwd / deconv [k,k,cout,cin] bwd
+        out = torch.zeros(big, k, 8, 4)
+        out[:, :, :k, :small] = w.permute(3, 0, 1, 2)
+        return out.reshape(big, k * 32).contiguous()
+
     lib = L.load()
     d = _layer_desc(layer)
-    w_fwd = scatter(True) if lib.cgs_pass_layout(C.byref(d), 0) == 1 else gather(*pack_map(layer, False), True)
-    w_bwd = scatter(False) if lib.cgs_pass_layout(C.byref(d), 1) == 1 else gather(*pack_map(layer, True), False)
+    kinds = {0: None, 1: scatter, 2: window}
+    lf, lb = lib.cgs_pass_layout(C.byref(d), 0), lib.cgs_pass_layout(C.byref(d), 1)
+    w_fwd = gather(*pack_map(layer, False), True) if lf == 0 else (scatter(True) if lf == 1 else window())
+    w_bwd = gather(*pack_map(layer, True), False) if lb == 0 else (scatter(False) if lb == 1 else window())
     return w_fwd, w_bwd, bias
 
 

@@ -428,6 +428,21 @@ conv_gemm_simt_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
     const int i = q - j * p.MW;
     const int cin = p.cblocks ? p.cblocks * BK : 4;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.window) {
+      for (int ky = 0; ky < gc.ntaps; ++ky) {
+        const int y = j * p.S + gc.dy[ky];
+        if ((unsigned)y >= (unsigned)p.IH) continue;
+        const float* src = p.in + ((size_t)(b * p.IH + y) * p.in_pitch_px + (i * 2 + p.win_x0)) * 4;
+        for (int q = 0; q < p.win_k * 4; ++q) {
+          const float a = __ldg(src + q);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int n = ng * 4 + u;
+            if (n < p.N) acc[u] = fmaf(a, __ldg(w + (size_t)n * w_cols + gc.k0 + ky * 32 + q), acc[u]);
+          }
+        }
+      }
+    } else
     for (int tp = 0; tp < gc.ntaps; ++tp) {
       const int y = j * p.S + gc.dy[tp];
       const int x = i * p.S + gc.dx[tp];
@@ -539,6 +554,20 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   p.a_tma = (p.cblocks > 0) && !(p.debug & 512);
   CUtensorMap tmap_a;
   std::memset(&tmap_a, 0, sizeof(tmap_a));
+  if (p.window) {
+    // overlapping-window view of the pitched image: dim0 = 32 floats (8 stored pixels), dim1 = output column i
+    // (every 2 pixels = 32 bytes), dim2 = input row (traversal stride 2), dim3 = image
+    if (p.MW > 256 || p.BH * 2 > 256) return set_error(CGS_ERR_UNSUPPORTED, "TMA box too large");
+    const cuuint64_t row_bytes = (cuuint64_t)p.in_pitch_px * 16;
+    cuuint64_t adim[4] = {32, (cuuint64_t)p.MW, (cuuint64_t)p.IH, (cuuint64_t)p.B};
+    cuuint64_t astr[3] = {32, row_bytes, (cuuint64_t)p.IH * row_bytes};
+    cuuint32_t abox[4] = {32, (cuuint32_t)p.MW, (cuuint32_t)(p.BH * 2), (cuuint32_t)p.BB};
+    cuuint32_t aest[4] = {1, 1, 2, 1};
+    CUresult ra = enc(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in) + p.win_x0 * 4, adim, astr,
+                      abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ra != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (window A operand) failed (%d)", (int)ra);
+  } else
   if (p.a_tma) {
     // input viewed as [B][IH][IW][Cs]; traversal strides S pick every S-th pixel, so a box of
     // {32 ch, MW*S, BH*S, BB} lands as BB*BH*MW rows of 128 bytes; out-of-range coordinates read zeros
@@ -576,6 +605,7 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
 int validate(const ConvGemmParams& p, int w_cols) {
   if (p.ON % 4 != 0) return set_error(CGS_ERR_INVALID, "output channel stride %d must be a multiple of 4", p.ON);
   if (p.cblocks == 0 && p.Cs != 4) return set_error(CGS_ERR_INVALID, "pixel mode needs channel stride 4");
+  if (p.window && (p.cblocks != 1 || p.in_pitch_px <= 0)) return set_error(CGS_ERR_INVALID, "bad window-mode parameters");
   if (p.nclasses < 1 || p.nclasses > kMaxClasses) return set_error(CGS_ERR_INVALID, "bad class count");
   if (w_cols % 4 != 0) return set_error(CGS_ERR_INVALID, "weight row length must be a multiple of 4 floats");
   for (int c = 0; c < p.nclasses; ++c) {

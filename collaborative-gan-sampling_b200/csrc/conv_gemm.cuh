@@ -54,7 +54,11 @@ struct ConvGemmParams {
   // tile geometry (filled by the launcher): a row tile = BB images x BH rows x MW columns of the M-space
   // (<= 128 rows, row r = (bb*BH + hh)*MW + ww), so that the A operand of a K block is ONE TMA box
   int B, BH, BB, hy_tiles, rows_valid;
-  int a_tma;          // 1: A tiles fetched by TMA (channel-block mode); 0: cp.async gather (pixel mode)
+  int a_tma;          // 1: A tiles fetched by TMA; 0: cp.async gather (pixel mode)
+  // window mode (strided pass over a <= 4-channel image stored with a zero-padded row pitch): K block ky of output
+  // pixel (j,i) is the 128 contiguous bytes starting at stored pixel (2j + ky - pad_y, 2i + win_x0); taps beyond the
+  // kernel width carry zero weights.  One TMA box per K block through an overlapping-window tensor map.
+  int window, win_k, win_x0, in_pitch_px;
   int nclasses;
   int epi, act;
   int first, clip, sgd;

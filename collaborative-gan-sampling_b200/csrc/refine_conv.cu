@@ -208,6 +208,86 @@ int make_backward_params(const cgs_layer_desc& L, int64_t B, const float* dy, fl
 
 
 // ---------------------------------------------------------------------------------------------
+// Image-like tensors (<= 4 channels: the generated image and its gradient) live in a PITCHED layout inside the
+// chain: [B][H][W + 8][4] with pixel x stored at column x + 2 and zero columns around it.  That lets the strided
+// passes over them ("window" lowering below) fetch a whole K block with one TMA box and makes horizontal padding
+// free; vertical padding is TMA out-of-bounds zero fill.  The public API stays dense: [B][H][W][4].
+// ---------------------------------------------------------------------------------------------
+constexpr int IMG_XOFF = 2;
+inline int img_pitch(int w) { return w + 8; }
+inline size_t tensor_elems(int h, int w, int c) {        // per-sample elements of an activation inside the chain
+  return c <= 4 ? (size_t)h * img_pitch(w) * 4 : (size_t)h * w * cstride(c);
+}
+
+// Window lowering: strided-type passes whose INPUT is image-like (first conv forward, last deconv data-gradient).
+bool use_window(const cgs_layer_desc& L, bool backward) {
+  return (L.type == CGS_LAYER_CONV && !backward && L.cin <= 4) || (L.type == CGS_LAYER_DECONV && backward && L.cout <= 4);
+}
+inline int window_kcols(const cgs_layer_desc& L) { return L.k * 32; }
+
+// in = pitched image-like tensor; K block ky = 8 stored pixels x 4 channels starting at (2j + ky - pad_y, 2i + x0)
+int make_window_params(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out,
+                       ConvGemmParams& p) {
+  if (int rc = check_layer(L)) return rc;
+  if (L.k > 8) return set_error(CGS_ERR_UNSUPPORTED, "window lowering needs k <= 8");
+  std::memset(&p, 0, sizeof(p));
+  const LayerShape s = layer_shape(L);
+  const int ih = backward ? s.hout : L.hin, iw = backward ? s.wout : L.win;      // image-like input
+  const int oh = backward ? L.hin : s.hout, ow = backward ? L.win : s.wout;      // output grid = M-space
+  const int pad_y = same_pad_before(ih, L.k), pad_x = same_pad_before(iw, L.k);
+  if (pad_x > IMG_XOFF) return set_error(CGS_ERR_UNSUPPORTED, "horizontal padding %d exceeds the image margin", pad_x);
+  p.in = in;
+  p.out = out;
+  p.bias = backward ? nullptr : L.bias;
+  p.epi = EPI_RAW;
+  p.N = backward ? L.cin : L.cout;
+  p.ON = cstride(p.N);
+  p.OH = oh; p.OW = ow;
+  p.IH = ih; p.IW = iw;
+  p.Cs = 4;
+  p.cblocks = 1;
+  p.MH = oh; p.MW = ow;
+  p.S = 2; p.os = 1;
+  p.nclasses = 1;
+  GemmClass& g = p.cls[0];
+  g.k0 = 0; g.oy0 = g.ox0 = 0;
+  g.ntaps = L.k; g.nkx = 1; g.nkb = L.k;
+  for (int ky = 0; ky < L.k; ++ky) { g.dy[ky] = (signed char)(ky - pad_y); g.dx[ky] = 0; }
+  p.window = 1;
+  p.win_k = L.k;
+  p.win_x0 = IMG_XOFF - pad_x;
+  p.in_pitch_px = img_pitch(iw);
+  p.M = (int)(B * p.MH * p.MW);
+  return CGS_OK;
+}
+
+// dense [B][H][W][4]  <->  pitched [B][H][W+8][4] (test entry points and API copies only)
+__global__ void __launch_bounds__(256) pad_image_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H,
+                                                        int W, long long rows) {
+  const int P = W + 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < rows * P;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % P);
+    const long long r = idx / P;
+    const int x = c - IMG_XOFF;
+    dst[idx] = (x >= 0 && x < W) ? src[r * W + x] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+int pad_image(const float* dense, float* pitched, int64_t B, int H, int W, cudaStream_t st) {
+  const long long rows = (long long)B * H;
+  long long blocks = (rows * (W + 8) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pad_image_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)dense, (float4*)pitched, H, W, rows); count_launch();
+  return check_launch("pad_image_kernel");
+}
+int unpad_image(const float* pitched, float* dense, int64_t B, int H, int W, cudaStream_t st) {
+  cudaError_t e = cudaMemcpy2DAsync(dense, (size_t)W * 16, pitched + IMG_XOFF * 4, (size_t)img_pitch(W) * 16, (size_t)W * 16,
+                                    (size_t)B * H, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+  return CGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Scatter formulation for transposed-type passes with <= 4 output channels (deconv -> image, conv1 data-gradient).
 // The gather form would re-read every input pixel k^2/4 * 4 times for a 1..3-wide output; instead
 //   stage 1  col[b,iy,ix,(ky,kx,c)] = sum_ci in[b,iy,ix,ci] * W[(ky,kx,c)][ci]     one GEMM, input read once
@@ -262,16 +342,22 @@ struct Col2imParams {
   const float* aux;
   int IH, IW, OH, OW, k, pad_y, pad_x, pitch;
   int epi, act, round_out;
-  long long pixels;      // B * OH * OW
+  int out_pitch, out_xoff;   // row pitch (pixels) and first data column of out / aux (dense: OW, 0)
+  long long pixels;          // B * OH * out_pitch (pad columns are written as zeros)
 };
 
 __global__ void __launch_bounds__(256) col2im_kernel(const Col2imParams p) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.pixels;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % p.OW);
-    const long long t = idx / p.OW;
+    const int xc = (int)(idx % p.out_pitch);
+    const long long t = idx / p.out_pitch;
     const int y = (int)(t % p.OH);
     const long long b = t / p.OH;
+    const int x = xc - p.out_xoff;
+    if (x < 0 || x >= p.OW) {                       // margin of the pitched layout
+      *reinterpret_cast<float4*>(p.out + idx * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ky = 0; ky < p.k; ++ky) {
       const int ty = y + p.pad_y - ky;
@@ -319,7 +405,7 @@ int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int
 
 // One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
 int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
-             float* col, int math, cudaStream_t st) {
+             float* col, int math, cudaStream_t st, bool dense_image = false) {
   const float* w = backward ? L.w_bwd : L.w_fwd;
   const int rows = backward ? L.rows_bwd : L.rows_fwd;
   const int cols = backward ? L.kcols_bwd : L.kcols_fwd;
@@ -348,14 +434,22 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
       c.IH = s.hout; c.IW = s.wout; c.OH = L.hin; c.OW = L.win;
       c.pad_y = same_pad_before(L.hin, L.k); c.pad_x = same_pad_before(L.win, L.k);
     }
-    c.pixels = (long long)B * c.OH * c.OW;
+    c.out_pitch = dense_image ? c.OW : img_pitch(c.OW);
+    c.out_xoff = dense_image ? 0 : IMG_XOFF;
+    c.pixels = (long long)B * c.OH * c.out_pitch;
     long long blocks = (c.pixels + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     col2im_kernel<<<(int)blocks, 256, 0, st>>>(c); count_launch();
     return check_launch("col2im_kernel");
   }
   ConvGemmParams p;
-  if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) return rc;
+  if (use_window(L, backward)) {
+    if (rows != (backward ? L.cin : L.cout) || cols != window_kcols(L))
+      return set_error(CGS_ERR_INVALID, "weights of this pass must be in window layout (%d columns)", window_kcols(L));
+    if (int rc = make_window_params(L, backward, B, in, out, p)) return rc;
+  } else if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) {
+    return rc;
+  }
   if (!backward) p.bias = L.bias;
   p.epi = e.epi;
   p.act = e.act;
@@ -389,7 +483,8 @@ struct HeadParams {
   float* best_img;      // [B, img_elems]
   const float* feature; // [B, feat_elems] current feature (only if best_feature wanted)
   float* best_feature;
-  int img_elems, feat_elems;
+  int img_elems, feat_elems;   // dense per-sample sizes (what the caller sees)
+  int img_h, img_w4, img_pitch4, img_xoff4;   // chain-side image layout in float4 units (pitched if <= 4 channels)
   float* cur_logit;     // [B]
   float* best_logit;    // [B]
   float* best_step;     // [B]
@@ -466,9 +561,13 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     }
   }
   if (s_update) {
-    const float4* src = reinterpret_cast<const float4*>(p.img + (size_t)b * p.img_elems);
+    // chain-side image rows (possibly pitched) -> dense best_img
+    const float4* src = reinterpret_cast<const float4*>(p.img) + (size_t)b * p.img_h * p.img_pitch4 + p.img_xoff4;
     float4* dst = reinterpret_cast<float4*>(p.best_img + (size_t)b * p.img_elems);
-    for (int i = threadIdx.x; i < p.img_elems / 4; i += 256) dst[i] = src[i];
+    for (int i = threadIdx.x; i < p.img_h * p.img_w4; i += 256) {
+      const int y = i / p.img_w4;
+      dst[i] = src[(size_t)y * p.img_pitch4 + (i - y * p.img_w4)];
+    }
     if (p.best_feature) {
       const float4* fs = reinterpret_cast<const float4*>(p.feature + (size_t)b * p.feat_elems);
       float4* fd = reinterpret_cast<float4*>(p.best_feature + (size_t)b * p.feat_elems);
@@ -502,6 +601,7 @@ static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& 
   if (c.head.type != CGS_LAYER_FC || c.head.cout != 1)
     return set_error(CGS_ERR_UNSUPPORTED, "discriminator must end in a linear layer with one logit");
   const cgs_layer_desc& L0 = c.layers[0];
+  if (L0.cin <= 4) return set_error(CGS_ERR_UNSUPPORTED, "the refined feature map must have >= 32 channels");
   c.act_elems[0] = (size_t)L0.hin * L0.win * cstride(L0.cin);
   c.max_elems = c.act_elems[0];
   c.col_elems = 0;
@@ -512,11 +612,11 @@ static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& 
       if (ce > c.col_elems) c.col_elems = ce;
     }
     const LayerShape s = layer_shape(c.layers[i]);
-    c.act_elems[i + 1] = (size_t)s.hout * s.wout * s.cs_out;
+    c.act_elems[i + 1] = tensor_elems(s.hout, s.wout, c.layers[i].cout);
     if (c.act_elems[i + 1] > c.max_elems) c.max_elems = c.act_elems[i + 1];
     if (i + 1 < c.n) {
       const cgs_layer_desc& Ln = c.layers[i + 1];
-      const size_t expect = (Ln.type == CGS_LAYER_FC) ? (size_t)Ln.cin : (size_t)Ln.hin * Ln.win * cstride(Ln.cin);
+      const size_t expect = (Ln.type == CGS_LAYER_FC) ? (size_t)Ln.cin : tensor_elems(Ln.hin, Ln.win, Ln.cin);
       if (expect != c.act_elems[i + 1])
         return set_error(CGS_ERR_INVALID, "layer %d output (%zu) does not feed layer %d input (%zu)", i,
                          c.act_elems[i + 1], i + 1, expect);
@@ -608,7 +708,17 @@ static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams
   hp.K = c.head.cin;
   hp.act = c.layers[c.n - 1].act;
   hp.img = w.act[c.n_gtail];
-  hp.img_elems = (int)c.act_elems[c.n_gtail];
+  {
+    const cgs_layer_desc& Li = c.layers[c.n_gtail - 1];          // producer of the image
+    const LayerShape si = layer_shape(Li);
+    const int c4 = si.cs_out / 4;
+    const bool pitched = Li.cout <= 4;
+    hp.img_h = si.hout;
+    hp.img_w4 = si.wout * c4;
+    hp.img_pitch4 = (pitched ? img_pitch(si.wout) : si.wout) * c4;
+    hp.img_xoff4 = pitched ? IMG_XOFF * c4 : 0;
+    hp.img_elems = si.hout * si.wout * si.cs_out;
+  }
   hp.feature = w.act[0];
   hp.feat_elems = (int)c.act_elems[0];
   hp.cur_logit = w.cur_logit;
@@ -706,33 +816,65 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   hp.dpre = grad_out ? w.g[0] : nullptr;
   if (int rc = head_launch(c, w, B, hp, st)) return rc;
   cudaMemcpyAsync(logit_out, w.cur_logit, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
-  if (img_out)
-    cudaMemcpyAsync(img_out, w.act[c.n_gtail], (size_t)B * c.act_elems[c.n_gtail] * 4, cudaMemcpyDeviceToDevice, st);
+  if (img_out) {
+    const cgs_layer_desc& Li = c.layers[c.n_gtail - 1];
+    const LayerShape si = layer_shape(Li);
+    if (Li.cout <= 4) {
+      if (int rc = unpad_image(w.act[c.n_gtail], img_out, B, si.hout, si.wout, st)) return rc;
+    } else {
+      cudaMemcpyAsync(img_out, w.act[c.n_gtail], (size_t)B * c.act_elems[c.n_gtail] * 4, cudaMemcpyDeviceToDevice, st);
+    }
+  }
   if (grad_out) {
     if (int rc = run_backward(c, w, B, math, nullptr, grad_out, st)) return rc;
   }
   return check_launch("cgs_forward_logits_and_grad");
 }
 
+static size_t layer_stage_elems(const cgs_layer_desc& L, bool backward) {   // pitched copy of an image-like input
+  if (!use_window(L, backward)) return 0;
+  const LayerShape s = layer_shape(L);
+  return backward ? tensor_elems(s.hout, s.wout, L.cout) : tensor_elems(L.hin, L.win, L.cin);
+}
+
 extern "C" size_t cgs_layer_workspace_bytes(const cgs_layer_desc* L, int64_t B) {
   if (!L || B < 0) return 0;
   size_t ce = scatter_col_elems(*L, false);
-  const size_t cb = scatter_col_elems(*L, true);
-  if (cb > ce) ce = cb;
-  return ce * (size_t)B * 4 + 256;
+  if (scatter_col_elems(*L, true) > ce) ce = scatter_col_elems(*L, true);
+  size_t se = layer_stage_elems(*L, false);
+  if (layer_stage_elems(*L, true) > se) se = layer_stage_elems(*L, true);
+  return (ce + se) * (size_t)B * 4 + 512;
+}
+
+// The single-layer entry points take and return DENSE tensors; image-like inputs of window-lowered passes are
+// re-laid out into the workspace first (inside the refinement chain they are produced pitched, no copy).
+static int layer_pass_dense(const cgs_layer_desc& L, bool backward, int math, int64_t B, const float* in, float* out,
+                            const PassEpi& e, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const bool needs_ws = use_scatter(L, backward) || use_window(L, backward);
+  if (needs_ws && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(&L, B)))
+    return set_error(CGS_ERR_WORKSPACE, "workspace too small");
+  float* base = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  float* col = base;
+  size_t ce = scatter_col_elems(L, false);
+  if (scatter_col_elems(L, true) > ce) ce = scatter_col_elems(L, true);
+  float* stage = base + ((ce * (size_t)B + 63) & ~size_t(63));
+  if (use_window(L, backward)) {
+    const LayerShape s = layer_shape(L);
+    const int h = backward ? s.hout : L.hin, w = backward ? s.wout : L.win;
+    if (int rc = pad_image(in, stage, B, h, w, st)) return rc;
+    in = stage;
+  }
+  return run_pass(L, backward, B, in, out, e, col, math, st, /*dense_image=*/true);
 }
 
 extern "C" int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y,
                                  void* workspace, size_t workspace_bytes, cgs_stream_t stream) {
   if (int rc = require_sm100()) return rc;
   if (!L || !x || !y) return set_error(CGS_ERR_INVALID, "null argument");
-  if (use_scatter(*L, false) && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(L, B)))
-    return set_error(CGS_ERR_WORKSPACE, "workspace too small");
   PassEpi e;
   e.epi = EPI_FWD;
   e.act = L->act;
-  float* col = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
-  return run_pass(*L, false, B, x, y, e, col, math, (cudaStream_t)stream);
+  return layer_pass_dense(*L, false, math, B, x, y, e, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, const float* dy, float* dx,
@@ -740,22 +882,21 @@ extern "C" int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, 
                                   cgs_stream_t stream) {
   if (int rc = require_sm100()) return rc;
   if (!L || !dy || !dx) return set_error(CGS_ERR_INVALID, "null argument");
-  if (use_scatter(*L, true) && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(L, B)))
-    return set_error(CGS_ERR_WORKSPACE, "workspace too small");
   PassEpi e;
   if (x_fwd && prev_act != CGS_ACT_NONE) {
     e.epi = EPI_BWD;
     e.aux = x_fwd;
     e.act = prev_act;
   }
-  float* col = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
-  return run_pass(*L, true, B, dy, dx, e, col, math, (cudaStream_t)stream);
+  return layer_pass_dense(*L, true, math, B, dy, dx, e, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // Host-only: 0 = the pass uses the gather layout described by cgs_pack_map, 1 = scatter layout
-// (rows = (ky*k + kx)*4 + small channel, K = the large channel count; see "Scatter formulation" above).
+// (rows = (ky*k + kx)*4 + small channel, K = the large channel count; see "Scatter formulation" above),
+// 2 = window layout (rows = large channel, K index = ky*32 + kx*4 + small channel, zero elsewhere).
 extern "C" int cgs_pass_layout(const cgs_layer_desc* L, int backward) {
   if (!L) return set_error(CGS_ERR_INVALID, "null layer");
+  if (use_window(*L, backward != 0)) return 2;
   return use_scatter(*L, backward != 0) ? 1 : 0;
 }
 
@@ -805,20 +946,22 @@ extern "C" int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* 
 
 // Host-only introspection (no GPU needed): the gathered-GEMM parameters a layer pass is lowered to, flattened to
 // int32 so tests can replay the exact gather on the CPU.  Layout: [IH, IW, Cs, cblocks, MH, MW, S, M, OH, OW, ON,
-// os, N, nclasses] then per class [k0, nkb, ntaps, oy0, ox0, dy[32], dx[32]].  Returns the number of ints.
+// os, N, nclasses, window, win_k, win_x0, in_pitch_px] then per class [k0, nkb, ntaps, oy0, ox0, dy[32], dx[32]].  Returns the number of ints.
 extern "C" int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
                                          int64_t capacity) {
   if (!L) return set_error(CGS_ERR_INVALID, "null layer");
   ConvGemmParams p;
-  int rc = use_scatter(*L, backward != 0) ? make_scatter_gemm_params(*L, backward != 0, B, nullptr, nullptr, p)
+  int rc = use_window(*L, backward != 0) ? make_window_params(*L, backward != 0, B, nullptr, nullptr, p)
+           : use_scatter(*L, backward != 0) ? make_scatter_gemm_params(*L, backward != 0, B, nullptr, nullptr, p)
            : backward ? make_backward_params(*L, B, nullptr, nullptr, p) : make_forward_params(*L, B, nullptr, nullptr, p);
   if (rc) return rc;
-  const int64_t need = 14 + (int64_t)p.nclasses * (5 + 2 * kMaxTaps);
+  const int64_t need = 18 + (int64_t)p.nclasses * (5 + 2 * kMaxTaps);
   if (!out) return need;
   if (capacity < need) return set_error(CGS_ERR_INVALID, "capacity too small");
   int32_t* o = out;
-  const int head[14] = {p.IH, p.IW, p.Cs, p.cblocks, p.MH, p.MW, p.S, p.M, p.OH, p.OW, p.ON, p.os, p.N, p.nclasses};
-  for (int i = 0; i < 14; ++i) *o++ = head[i];
+  const int head[18] = {p.IH, p.IW, p.Cs, p.cblocks, p.MH, p.MW, p.S, p.M, p.OH, p.OW, p.ON, p.os, p.N, p.nclasses,
+                        p.window, p.win_k, p.win_x0, p.in_pitch_px};
+  for (int i = 0; i < 18; ++i) *o++ = head[i];
   for (int c = 0; c < p.nclasses; ++c) {
     const GemmClass& g = p.cls[c];
     *o++ = g.k0; *o++ = g.nkb; *o++ = g.ntaps; *o++ = g.oy0; *o++ = g.ox0;

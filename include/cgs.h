@@ -212,12 +212,13 @@ CGS_API int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* ky,
                              int64_t capacity);
 
 /* Host-only introspection: the gathered-GEMM parameters a layer pass is lowered to, as int32s
- * [IH, IW, Cs, cblocks, MH, MW, S, M, OH, OW, ON, os, N, nclasses] + per class [k0, nkb, ntaps, oy0, ox0, dy[32],
+ * [IH, IW, Cs, cblocks, MH, MW, S, M, OH, OW, ON, os, N, nclasses, window, win_k, win_x0, in_pitch_px] + per class [k0, nkb, ntaps, oy0, ox0, dy[32],
  * dx[32]] (see csrc/conv_gemm.cuh).  NULL `out` queries the length.  Lets tests replay the gather on the CPU. */
 CGS_API int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
                                       int64_t capacity);
 
-/* Lowering of a pass: 0 = gather layout (K order given by cgs_pack_map), 1 = scatter layout.  Transposed-type
+/* Lowering of a pass: 0 = gather layout (K order given by cgs_pack_map), 1 = scatter layout, 2 = window layout
+ * (strided passes reading a <= 4-channel image: rows = large channel, K index = ky*32 + kx*4 + small channel).  Transposed-type
  * passes with <= 4 output channels (deconv -> image forward, first-conv data-gradient) run as one GEMM over the
  * input pixels producing all k*k taps, followed by a col2im kernel with the fused epilogue; their packed matrix
  * has rows = (ky*k + kx)*4 + small_channel and K = the large channel count.  Host only. */

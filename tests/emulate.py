@@ -21,9 +21,10 @@ def gemm_params(layer, backward, B):
     n = L.check(lib.cgs_debug_gemm_params(C.byref(d), int(backward), B, None, 0))
     buf = np.zeros(n, np.int32)
     L.check(lib.cgs_debug_gemm_params(C.byref(d), int(backward), B, buf.ctypes.data, n))
-    keys = ["IH", "IW", "Cs", "cblocks", "MH", "MW", "S", "M", "OH", "OW", "ON", "os", "N", "nclasses"]
-    p = dict(zip(keys, buf[:14].tolist()))
-    off = 14
+    keys = ["IH", "IW", "Cs", "cblocks", "MH", "MW", "S", "M", "OH", "OW", "ON", "os", "N", "nclasses",
+            "window", "win_k", "win_x0", "in_pitch_px"]
+    p = dict(zip(keys, buf[:18].tolist()))
+    off = 18
     p["cls"] = []
     for _ in range(p["nclasses"]):
         k0, nkb, ntaps, oy0, ox0 = buf[off:off + 5].tolist()
@@ -95,9 +96,36 @@ def col2im(col, layer, backward, B):
     return out
 
 
+IMG_XOFF = 2
+
+
+def replay_window(p, x_dense, w, B):
+    """Window lowering: x_dense [B, IH, IW, 4] is re-laid out pitched ([IH][IW+8][4], data at column 2) and every
+    K block ky of output pixel (j, i) is the 32 contiguous floats at stored pixel (2j + dy[ky], 2i + win_x0)."""
+    IH, IW, P = p["IH"], p["IW"], p["in_pitch_px"]
+    assert P == IW + 8
+    img = np.zeros((B, IH, P, 4))
+    img[:, :, IMG_XOFF:IMG_XOFF + IW, :] = np.asarray(x_dense, np.float64).reshape(B, IH, IW, 4)
+    flat = img.reshape(B, IH, P * 4)
+    g = p["cls"][0]
+    w = np.asarray(w, np.float64)
+    out = np.zeros((B, p["OH"], p["OW"], p["ON"]))
+    for j in range(p["MH"]):
+        for ky in range(g["ntaps"]):
+            y = j * p["S"] + g["dy"][ky]
+            if not 0 <= y < IH:
+                continue
+            for i in range(p["MW"]):
+                s0 = (2 * i + p["win_x0"]) * 4
+                out[:, j, i, :p["N"]] += flat[:, y, s0:s0 + 32] @ w[:p["N"], ky * 32:(ky + 1) * 32].T
+    return out
+
+
 def layer_pass(layer, backward, B, x_padded, w_packed):
     """Raw accumulators of one pass, replayed on the CPU whichever lowering the library picks."""
     p = gemm_params(layer, backward, B)
+    if pass_layout(layer, backward) == 2:
+        return replay_window(p, x_padded, w_packed, B)
     if pass_layout(layer, backward) == 1:
         col = replay(p, np.asarray(x_padded, np.float64).reshape(p["M"], 1, 1, p["Cs"]), w_packed, p["M"])
         return col2im(col.reshape(p["M"], p["ON"]), layer, backward, B)
