@@ -334,69 +334,80 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       int ro[PASSES];                              // row offsets of the rows this lane stores
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) ro[ps] = __shfl_sync(0xffffffffu, row_off, ps * ROWS_PER_PASS + rsub);
-      mbar_wait(&tmem_full_bar[acc], acc_ph);
-      if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      // last chunk index owned by this warp (it releases the accumulator after loading it)
       constexpr int NCH = BN / EPI_CH;
-      int last_own = -1;
-      for (int ch = group; ch < NCH; ch += ngroups) last_own = ch;
-      if (last_own < 0) {                          // nothing to do for this warp on such narrow tiles
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      }
-#pragma unroll 1
-      for (int ch = group; ch < NCH; ch += ngroups) {
-        const int c0 = ch * EPI_CH;
-        uint32_t v[EPI_CH];
-        tmem_ld_32x32b_x16(taddr + c0, v);
-        tmem_ld_wait();
-        if (ch == last_own) {
-          // all TMEM reads of this warp for this accumulator are done: hand it back before the global-memory part
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
-        }
-        const int nbase = n_tile * BN + c0;
-        if (nbase >= p.ON || (p.debug & 16)) continue;        // warp-uniform
-        // lane = row: stage 32 rows x 16 columns, then re-read with lane = (row group, 16-byte column)
-#pragma unroll
-        for (int q4 = 0; q4 < Q; ++q4)
-          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + q4 * 4) =
-              make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
-                          __uint_as_float(v[4 * q4 + 3]));
-        __syncwarp();
-        const int n = nbase + c4 * 4;
-        const bool n_ok = n < p.ON;                // ON is a multiple of 4
-        // issue every global read of the pass set first (independent loads in flight), then compute + store
-        float4 x0[PASSES], x1[PASSES];
+      // chunks pulled out of TMEM per batch (2 x 16 registers); narrow tiles finish in a single batch
+      constexpr int MAXOWN = ((NCH + 2) / 3) < 2 ? ((NCH + 2) / 3) : 2;
+      // epilogue operands (bias / forward output / feature + momentum) of a chunk, fetched ahead of its use
+      float4 x0[PASSES], x1[PASSES];
+      auto prefetch = [&](int ch) {
+        const int n = n_tile * BN + ch * EPI_CH + c4 * 4;
+        if (ch >= NCH || n >= p.ON) return;
         if (p.epi == EPI_BWD) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
-            if (ro[ps] >= 0 && n_ok) x0[ps] = __ldg(reinterpret_cast<const float4*>(p.aux + ro[ps] + n));
+            if (ro[ps] >= 0) x0[ps] = __ldg(reinterpret_cast<const float4*>(p.aux + ro[ps] + n));
         } else if (p.epi == EPI_UPDATE) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
-            if (ro[ps] >= 0 && n_ok) {
+            if (ro[ps] >= 0) {
               x0[ps] = *reinterpret_cast<const float4*>(p.out + ro[ps] + n);
               if (!p.sgd && !p.first) x1[ps] = *reinterpret_cast<const float4*>(p.mom + ro[ps] + n);
             }
         } else if (p.epi == EPI_FWD) {
-          x0[0] = (p.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x0[0] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      prefetch(group);                             // in flight while the main loop of this tile still runs
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      bool released = false;
+#pragma unroll 1
+      for (int ch0 = group; ch0 < NCH || !released; ch0 += ngroups * MAXOWN) {
+        // pull a batch of this warp's chunks out of TMEM at once, then give the accumulator back before touching
+        // global memory (the next-but-one tile's MMAs are waiting for it)
+        uint32_t v[MAXOWN][EPI_CH];
+#pragma unroll
+        for (int u = 0; u < MAXOWN; ++u)
+          if (ch0 + u * ngroups < NCH) tmem_ld_32x32b_x16(taddr + (ch0 + u * ngroups) * EPI_CH, v[u]);
+        tmem_ld_wait();
+        if (ch0 + ngroups * MAXOWN >= NCH) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
+          released = true;
         }
 #pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) {
-          if (ro[ps] >= 0 && n_ok) {
-            const int rr = ps * ROWS_PER_PASS + rsub;
-            const float4 a = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + c4 * 4);
-            const float4 o = epilogue4(p, ro[ps] + n, a, p.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
-            *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o;
-          }
+        for (int u = 0; u < MAXOWN; ++u) {
+          const int ch = ch0 + u * ngroups;
+          if (ch >= NCH) break;
+          const int nbase = n_tile * BN + ch * EPI_CH;
+          if (nbase >= p.ON || (p.debug & 16)) continue;        // warp-uniform
+          // lane = row: stage 32 rows x 16 columns, then re-read with lane = (row group, 16-byte column)
+#pragma unroll
+          for (int q4 = 0; q4 < Q; ++q4)
+            *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + q4 * 4) =
+                make_float4(__uint_as_float(v[u][4 * q4]), __uint_as_float(v[u][4 * q4 + 1]),
+                            __uint_as_float(v[u][4 * q4 + 2]), __uint_as_float(v[u][4 * q4 + 3]));
+          __syncwarp();
+          const int n = nbase + c4 * 4;
+          const bool n_ok = n < p.ON;                // ON is a multiple of 4
+          float4 a[PASSES];
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps)
+            a[ps] = *reinterpret_cast<const float4*>(stage + (ps * ROWS_PER_PASS + rsub) * EPI_PITCH + c4 * 4);
+          float4 o[PASSES];
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps)
+            if (ro[ps] >= 0 && n_ok) o[ps] = epilogue4(p, ro[ps] + n, a[ps], p.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
+          if (!(p.debug & 2048)) prefetch(ch + ngroups);   // operands of the next chunk: overlap with these stores
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps)
+            if (ro[ps] >= 0 && n_ok && !(p.debug & 1024)) *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o[ps];
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (warp == 0 && lane == 0) trace(p, 3, 2, tile_count);
     }
