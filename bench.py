@@ -114,6 +114,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # CPU oracle port (cpu_baseline / --impl reference)
 # ----------------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU arm undoes that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_step(arch_name, gain, batch, refine_steps, method, rate, seed=0):
     """One hot-path pass on the host: oracle graph refiner (FP32 torch-CPU restatement of
     sampling/collaborator.py over the nsgan nets, D BN in inference mode) + oracle MH chain.  Returns seconds."""
@@ -122,6 +130,8 @@ def cpu_port_step(arch_name, gain, batch, refine_steps, method, rate, seed=0):
     from oracle import graph_refiner as gr
     from oracle import nets as onets
     from oracle import sampling_np as snp
+    if torch.get_num_threads() != host_threads():
+        torch.set_num_threads(host_threads())
     arch = onets.get_arch(arch_name)
     w = onets.scale_weights_for_signal(arch, onets.init_weights(arch, seed=2019), gain)
     w = {k: torch.from_numpy(v) for k, v in w.items()}
