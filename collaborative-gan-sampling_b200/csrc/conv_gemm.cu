@@ -613,6 +613,11 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   return CGS_OK;
 }
 
+void derive_act(ConvGemmParams& p) {
+  p.act_tanh = (p.act == ACT_TANH);
+  p.slope = p.act == ACT_RELU ? 0.f : (p.act == ACT_LRELU ? 0.2f : 1.f);
+}
+
 int validate(const ConvGemmParams& p, int w_cols) {
   if (p.ON % 4 != 0) return set_error(CGS_ERR_INVALID, "output channel stride %d must be a multiple of 4", p.ON);
   if (p.cblocks == 0 && p.Cs != 4) return set_error(CGS_ERR_INVALID, "pixel mode needs channel stride 4");
@@ -637,7 +642,9 @@ int debug_trace_read(unsigned long long* out, int cap) {
   return n;
 }
 
-int launch_conv_gemm_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
+int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
+  ConvGemmParams p = p_in;
+  derive_act(p);
   if (int rc = validate(p, w_cols)) return rc;
   if (p.M <= 0) return CGS_OK;
   static int num_sms = 0;
@@ -655,8 +662,10 @@ int launch_conv_gemm_tc(const ConvGemmParams& p, const float* w, int w_rows, int
   }
 }
 
-int launch_conv_gemm_simt(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
+int launch_conv_gemm_simt(const ConvGemmParams& p_in, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   (void)w_rows;
+  ConvGemmParams p = p_in;
+  derive_act(p);
   if (int rc = validate(p, w_cols)) return rc;
   if (p.M <= 0) return CGS_OK;
   const long long total = (long long)p.nclasses * p.M * (p.ON / 4);

@@ -63,6 +63,8 @@ struct ConvGemmParams {
   int epi, act;
   int first, clip, sgd;
   float rate, alpha, vmin, vmax;
+  float slope;        // derived from act by the launcher: relu 0, lrelu 0.2, none 1 (branch-free epilogue)
+  int act_tanh;       // act == tanh (slow path)
   int round_out;      // round results to TF32 (RN) because the next consumer is a kind::tf32 MMA
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
   GemmClass cls[kMaxClasses];
@@ -98,15 +100,21 @@ __device__ __forceinline__ float tf32_rn(float x) {
 __device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, float4 a, float4 x0, float4 x1) {
   float4 o = a;
   if (p.epi == EPI_FWD) {
-    o.x = act_apply(a.x + x0.x, p.act);
-    o.y = act_apply(a.y + x0.y, p.act);
-    o.z = act_apply(a.z + x0.z, p.act);
-    o.w = act_apply(a.w + x0.w, p.act);
+    const float vx = a.x + x0.x, vy = a.y + x0.y, vz = a.z + x0.z, vw = a.w + x0.w;
+    if (!p.act_tanh) {          // relu / lrelu / none: max(v, slope * v)
+      o.x = fmaxf(vx, vx * p.slope); o.y = fmaxf(vy, vy * p.slope);
+      o.z = fmaxf(vz, vz * p.slope); o.w = fmaxf(vw, vw * p.slope);
+    } else {
+      o.x = tanhf(vx); o.y = tanhf(vy); o.z = tanhf(vz); o.w = tanhf(vw);
+    }
   } else if (p.epi == EPI_BWD) {
-    o.x = a.x * act_grad_from_output(x0.x, p.act);
-    o.y = a.y * act_grad_from_output(x0.y, p.act);
-    o.z = a.z * act_grad_from_output(x0.z, p.act);
-    o.w = a.w * act_grad_from_output(x0.w, p.act);
+    if (!p.act_tanh) {          // derivative through the forward output: 1 where it is positive, slope elsewhere
+      o.x = a.x * (x0.x > 0.f ? 1.f : p.slope); o.y = a.y * (x0.y > 0.f ? 1.f : p.slope);
+      o.z = a.z * (x0.z > 0.f ? 1.f : p.slope); o.w = a.w * (x0.w > 0.f ? 1.f : p.slope);
+    } else {
+      o.x = a.x * (1.f - x0.x * x0.x); o.y = a.y * (1.f - x0.y * x0.y);
+      o.z = a.z * (1.f - x0.z * x0.z); o.w = a.w * (1.f - x0.w * x0.w);
+    }
   } else if (p.epi == EPI_UPDATE) {
     // sampling/policy.py:27-37; separately rounded multiplies / adds like the reference's un-fused TF ops
     float4 m;
