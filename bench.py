@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the K-step sequence eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -271,7 +272,7 @@ def run_ours(args, wl):
     arch = N.get_arch(arch_name)
     weights = S.init_weights(arch, seed=2019, gain=gain)
     spec = N.NetSpec(arch, weights, dev, math=args.math)
-    refiner = Refiner(ksteps, rate, method)
+    refiner = Refiner(ksteps, rate, method, cuda_graph=not args.no_graph)
     refiner.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     mh = IndependenceSampler(T=20, rng="philox", seed=2019)          # nsgan/GAN.py:169
     mh.set_score_curr(np.float32(0.5))
@@ -385,6 +386,7 @@ def run_ours(args, wl):
                        "global_batch": world * batch, "parallelism": "dp%d (sharded batch, no collective in the K loop)" % world,
                        "l2": "flushed (256 MiB write) between timed iterations; per-step working set also exceeds L2",
                        "weights": "random init seed 2019, gain %.1f" % gain,
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of the K-step kernel sequence",
                        "gflop_per_sample": round(flops_sample / 1e9, 3)},
             "tflops_algorithmic": round(world * batch * flops_sample / (total_s / args.steps) / 1e12, 2),
             "accepted_per_step": int(n_acc),

@@ -30,7 +30,7 @@ from cgs import runtime as R
 
 
 class Refiner():
-    def __init__(self, rollout_steps, rollout_rate, rollout_method="momentum", math=None):
+    def __init__(self, rollout_steps, rollout_rate, rollout_method="momentum", math=None, cuda_graph=False):
         self.forward_steps = rollout_steps
         self.optimizer = PolicyAdaptive(rollout_rate, rollout_method)
         self.log = False
@@ -38,6 +38,8 @@ class Refiner():
         self.vmax = None
         self.math = math
         self.early_exit_logit = None      # opt-in (README.md:13); None = reference behaviour (best of K)
+        self.cuda_graph = cuda_graph      # capture the K-step launch sequence once per batch shape and replay it
+        self._graphs = {}
         self._ws = R.Workspace()
         self.real_logits = None
         self.real_logits_mean = None
@@ -120,17 +122,11 @@ class Refiner():
         if tuple(feat_in.shape[1:]) != self._spec.feature_shape:
             raise ValueError("feature shape %s does not match the spec %s" % (tuple(feat_in.shape[1:]), self._spec.feature_shape))
         B = feat_in.shape[0]
-        feat = feat_in.clone()                                    # tf.identity (collaborator.py:48,58)
-        best_img = torch.empty(self._img_shape(B), dtype=torch.float32, device=dev)
-        best_logit = torch.empty(B, dtype=torch.float32, device=dev)
-        best_step = torch.empty(B, dtype=torch.float32, device=dev)
-        default_logit = torch.empty(B, dtype=torch.float32, device=dev)
-        best_feat = torch.empty_like(feat) if keep_optimal_feature else None
-        idx = None
+        idx_host = None
         if mode == 'probabilistic':
             if prob_indices is None:
                 prob_indices = np.random.randint(self.forward_steps + 1, size=B)      # collaborator.py:56
-            idx, _ = R.to_device(np.asarray(prob_indices, dtype=np.int32), torch.int32, dev)
+            idx_host = np.asarray(prob_indices, dtype=np.int32)
         cfg = L.RefineCfg()
         cfg.steps = int(self.forward_steps)
         cfg.rate = float(self.optimizer.lambda_)
@@ -143,10 +139,58 @@ class Refiner():
         cfg.math = L.MATH_IDS[self.math]
         cfg.early_exit = 0 if self.early_exit_logit is None else 1
         cfg.exit_logit = float(self.early_exit_logit or 0.0)
-        ws = self._workspace(B, dev)
-        L.check(lib.cgs_refine_conv(C.byref(self._g.desc), C.byref(self._d.desc), C.byref(cfg), B, L.ptr(feat),
-                                    L.ptr(best_img), L.ptr(best_logit), L.ptr(best_step), L.ptr(default_logit),
-                                    L.ptr(idx), L.ptr(best_feat), L.ptr(ws), ws.numel(), L.stream_ptr()))
+
+        def buffers():
+            b = dict(feat=torch.empty_like(feat_in),
+                     best_img=torch.empty(self._img_shape(B), dtype=torch.float32, device=dev),
+                     best_logit=torch.empty(B, dtype=torch.float32, device=dev),
+                     best_step=torch.empty(B, dtype=torch.float32, device=dev),
+                     default_logit=torch.empty(B, dtype=torch.float32, device=dev),
+                     best_feat=torch.empty_like(feat_in) if keep_optimal_feature else None,
+                     idx=torch.empty(B, dtype=torch.int32, device=dev) if mode == 'probabilistic' else None)
+            return b
+
+        def launch(b, ws):
+            L.check(lib.cgs_refine_conv(C.byref(self._g.desc), C.byref(self._d.desc), C.byref(cfg), B, L.ptr(b["feat"]),
+                                        L.ptr(b["best_img"]), L.ptr(b["best_logit"]), L.ptr(b["best_step"]),
+                                        L.ptr(b["default_logit"]), L.ptr(b["idx"]), L.ptr(b["best_feat"]), L.ptr(ws),
+                                        ws.numel(), L.stream_ptr()))
+
+        if not self.cuda_graph:
+            b = buffers()
+            b["feat"].copy_(feat_in)                                  # tf.identity (collaborator.py:48,58)
+            if idx_host is not None:
+                b["idx"].copy_(torch.from_numpy(idx_host))
+            launch(b, self._workspace(B, dev))
+        else:
+            # the launch sequence depends only on (shapes, config): capture it once, replay afterwards
+            key = (B, mode, cfg.steps, cfg.rate, cfg.method, cfg.alpha, cfg.clip, cfg.vmin, cfg.vmax, cfg.math,
+                   cfg.early_exit, cfg.exit_logit, keep_optimal_feature)
+            ent = self._graphs.get(key)
+            if ent is None:
+                b = buffers()
+                nbytes = lib.cgs_refine_workspace_bytes(C.byref(self._g.desc), C.byref(self._d.desc), B)
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                b["feat"].copy_(feat_in)
+                if idx_host is not None:
+                    b["idx"].copy_(torch.from_numpy(idx_host))
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    launch(b, ws)                                     # warm-up outside capture (one-time attribute setup)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch(b, ws)
+                ent = self._graphs[key] = (graph, b, ws)
+            graph, sb, _ = ent
+            sb["feat"].copy_(feat_in)
+            if idx_host is not None:
+                sb["idx"].copy_(torch.from_numpy(idx_host))
+            graph.replay()
+            b = {k: (v.clone() if v is not None else None) for k, v in sb.items()}   # results outlive the next replay
+        feat, best_img, best_logit, best_step = b["feat"], b["best_img"], b["best_logit"], b["best_step"]
+        default_logit, best_feat = b["default_logit"], b["best_feat"]
         self.optimizer.reset_moving_average()                       # collaborator.py:86
         self.current_feature = feat
         self.default_logit = default_logit

@@ -159,3 +159,20 @@ def test_probabilistic_mode_and_clip(cgs_lib, cuda_device):
         r3.build_refiner(h0.to(cuda_device), None)
     with pytest.raises(NotImplementedError):
         ref.build_refiner(h0.to(cuda_device), None, "greedy")
+
+
+def test_cuda_graph_replay_is_bit_identical(cgs_lib, cuda_device):
+    """cuda_graph=True replays the captured K-step launch sequence: same bits as eager launches, call after call."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("mnist", 9, 3.0, cuda_device, "tf32")
+    eager = Refiner(4, 0.1)
+    graph = Refiner(4, 0.1, cuda_graph=True)
+    for r in (eager, graph):
+        r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    for seed in (1, 2, 3):
+        h0 = torch.relu(torch.randn(33, *arch["feature_shape"], generator=torch.Generator().manual_seed(seed))).to(cuda_device)
+        a = eager.build_refiner(h0)
+        b = graph.build_refiner(h0)
+        assert torch.equal(a, b) and torch.equal(eager.optimal_logit, graph.optimal_logit)
+        assert torch.equal(eager.optimal_step, graph.optimal_step) and torch.equal(eager.current_feature, graph.current_feature)
