@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgs.so")
+LIB_PATH = os.environ.get("CGS_LIB_PATH") or os.path.join(_HERE, "libcgs.so")   # override: A/B experiments only
 
 CGS_OK, CGS_ERR_INVALID, CGS_ERR_UNSUPPORTED, CGS_ERR_CUDA, CGS_ERR_WORKSPACE = 0, -1, -2, -3, -4
 POLICY_SGD, POLICY_MOMENTUM, POLICY_LADAM = 0, 1, 2

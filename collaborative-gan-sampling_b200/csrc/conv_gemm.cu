@@ -40,8 +40,9 @@ constexpr int BK = 32;                       // floats per K block = one 128-byt
 constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 8;
 constexpr int kMmaWarp = kEpiWarps + kProdWarps;       // 12
-constexpr int kTmaWarp = kMmaWarp + 1;                 // 13
-constexpr int kThreads = (kTmaWarp + 1) * 32;          // 448
+constexpr int kTmaWarp = kMmaWarp + 1;                 // 13: weight tiles
+constexpr int kTmaWarpA = kMmaWarp + 2;                // 14: A tiles (TMA mode)
+constexpr int kThreads = (kTmaWarpA + 1) * 32;         // 480
 constexpr int kRowsPerThread = BM / (kProdWarps * 4);  // 4
 constexpr int A_ATOM_BYTES = BM * BK * 4;    // 16 KB: 128 rows x one 128-byte swizzle row
 constexpr int EPI_CH = 16;                   // accumulator columns per TMEM load / staging pass
@@ -86,8 +87,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      // TMA mode: the TMA thread's arrive.expect_tx only; gather mode: + the async arrive of every producer thread
-      mbar_init(&full_bar[s], p.a_tma ? 1 : kProdWarps * 32 + 1);
+      // TMA mode: one arrive.expect_tx from each of the two TMA warps; gather mode: weight TMA warp + the async
+      // arrive of every producer thread
+      mbar_init(&full_bar[s], p.a_tma ? 2 : kProdWarps * 32 + 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -97,10 +99,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-  if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    if (p.a_tma) tma_prefetch_desc(&tmap_a);
-  }
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == kTmaWarpA && lane == 0 && p.a_tma) tma_prefetch_desc(&tmap_a);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -199,56 +199,79 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     }
     }  // !a_tma
   } else if (warp == kTmaWarp) {
-    // ------------------------------------------------------------------ TMA producer (weights, and A tiles in TMA mode)
-    // whole warp walks the loop (uniform control flow); one elected lane issues
+    // ------------------------------------------------------------------ TMA producer: weight tiles
+    // whole warp walks the loop (uniform control flow); one elected lane issues.  The weight matrix is viewed as
+    // {32, rows, K/32} so ONE box {32, BN, KB} fetches all K atoms of a stage as consecutive atom tiles.
     const uint32_t smem_b_u32 = smem_u32(smem_b);
-    const uint32_t smem_a_u32 = smem_u32(smem_a);
     uint32_t it_global = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ci = tile / tiles_per_class;
       const int rem = tile - ci * tiles_per_class;
-      const int m_tile = rem / p.n_tiles;
       const int n_tile = rem % p.n_tiles;
-      const GemmClass& gc = p.cls[ci];
-      const int k0 = gc.k0;
-      const int nkb = gc.nkb;
-      const int b0 = (m_tile / p.hy_tiles) * p.BB;
-      const int y_tile = (m_tile % p.hy_tiles) * p.BH * p.S;
-      const uint32_t a_bytes = p.a_tma ? (uint32_t)p.rows_valid * 128u : 0u;
-      int t = 0, cb = 0;
+      const int katom0 = p.cls[ci].k0 / BK;
+      const int nkb = p.cls[ci].nkb;
       for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
         const int s = it_global % C::STAGES;
         const uint32_t ph = (it_global / C::STAGES) & 1;
-        const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           trace(p, 1, 0, it_global);
           if (p.debug & 2) {
             mbar_arrive(&full_bar[s]);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * (C::B_ATOM_BYTES + a_bytes));
-            int tt = t, cc = cb;
-#pragma unroll
-            for (int a = 0; a < C::KB; ++a) {
-              if (a >= na) break;
-              tma_load_2d(smem_b_u32 + s * C::B_STAGE_BYTES + a * C::B_ATOM_BYTES, &tmap_w, &full_bar[s],
-                          k0 + (kb + a) * BK, n_tile * BN);
-              if (p.a_tma)   // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
-                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s], cc * BK,
-                            gc.dx[tt], y_tile + gc.dy[tt], b0);
-              if (++cc == p.cblocks) {
-                cc = 0;
-                ++tt;
-              }
-            }
+            mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
+            tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], 0, n_tile * BN, katom0 + kb);
           }
         }
         __syncwarp();
-        for (int a = 0; a < na; ++a)
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++t;
+      }
+    }
+  } else if (warp == kTmaWarpA) {
+    // ------------------------------------------------------------------ TMA producer: A tiles (TMA mode only)
+    if (p.a_tma) {
+      const uint32_t smem_a_u32 = smem_u32(smem_a);
+      const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
+      uint32_t it_global = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ci = tile / tiles_per_class;
+        const int rem = tile - ci * tiles_per_class;
+        const int m_tile = rem / p.n_tiles;
+        const GemmClass& gc = p.cls[ci];
+        const int nkb = gc.nkb;
+        const int b0 = (m_tile / p.hy_tiles) * p.BB;
+        const int y_tile = (m_tile % p.hy_tiles) * p.BH * p.S;
+        int t = 0, cb = 0;
+        for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
+          const int s = it_global % C::STAGES;
+          const uint32_t ph = (it_global / C::STAGES) & 1;
+          const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
+            if (p.debug & 2) {
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * a_bytes);
+              int tt = t, cc = cb;
+#pragma unroll
+              for (int a = 0; a < C::KB; ++a) {
+                if (a >= na) break;
+                // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
+                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s], cc * BK,
+                            gc.dx[tt], y_tile + gc.dy[tt], b0);
+                if (++cc == p.cblocks) {
+                  cc = 0;
+                  ++tt;
+                }
+              }
+            }
           }
+          __syncwarp();
+          for (int a = 0; a < na; ++a)
+            if (++cb == p.cblocks) {
+              cb = 0;
+              ++t;
+            }
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -534,11 +557,12 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
-  cuuint64_t gdim[2] = {(cuuint64_t)w_cols, (cuuint64_t)w_rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)w_cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), gdim, gstride, box, estr,
+  // weights [rows][K] viewed as {32 (k inside an atom), rows, K/32 (atom)}: a box {32, BN, KB} lands as KB atom tiles
+  cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)w_rows, (cuuint64_t)(w_cols / BK)};
+  cuuint64_t gstride[2] = {(cuuint64_t)w_cols * sizeof(float), (cuuint64_t)BK * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, (cuuint32_t)C::KB};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -623,7 +647,7 @@ int validate(const ConvGemmParams& p, int w_cols) {
   if (p.cblocks == 0 && p.Cs != 4) return set_error(CGS_ERR_INVALID, "pixel mode needs channel stride 4");
   if (p.window && (p.cblocks != 1 || p.in_pitch_px <= 0)) return set_error(CGS_ERR_INVALID, "bad window-mode parameters");
   if (p.nclasses < 1 || p.nclasses > kMaxClasses) return set_error(CGS_ERR_INVALID, "bad class count");
-  if (w_cols % 4 != 0) return set_error(CGS_ERR_INVALID, "weight row length must be a multiple of 4 floats");
+  if (w_cols % 32 != 0) return set_error(CGS_ERR_INVALID, "weight row length must be a multiple of 32 floats");
   for (int c = 0; c < p.nclasses; ++c) {
     if (p.cls[c].ntaps > kMaxTaps) return set_error(CGS_ERR_INVALID, "too many taps");
     if (p.cls[c].k0 + p.cls[c].nkb * BK > w_cols) return set_error(CGS_ERR_INVALID, "class K range exceeds weight matrix");
