@@ -363,9 +363,18 @@ def run_ours(args, wl):
             f_step, t_step, rows = roofline_profile(torch, spec, arch, batch, args.math, dev)
             achieved = f_step / t_step / 1e12
             peak = 0.5 * bf16_peak
+            traffic, ncu_tensor = None, None
+            tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
+            if os.path.exists(tpath) and batch == 1024:
+                with open(tpath) as f:
+                    tj = json.load(f).get("dcgan64" if arch_name == "dcgan64_l1" else arch_name)
+                if tj:
+                    traffic, ncu_tensor = int(tj["traffic_bytes"]), tj["tensor_pipe_active_pct_time_weighted"]
             roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 kind::tf32, all layer passes of one step)",
                     "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": None,
+                    "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write summed over the same launch set, ncu capture in profiles/round1_traffic.json",
+                    "ncu_tensor_pipe_active_pct": ncu_tensor,
                     "peak_source": "0.5 x %s (TF32 = half the BF16 rate)" % src,
                     "cublas_tf32_tflops_same_run": round(tf32_cublas, 1),
                     "frac_of_cublas_tf32": round(achieved / tf32_cublas, 4),
