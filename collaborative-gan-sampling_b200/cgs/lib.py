@@ -83,6 +83,7 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "cgs_refine_mlp2d": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(Refine2dCfg), C.c_void_p, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgs_refine_max_batch": (C.c_int64, [C.POINTER(NetDesc), C.POINTER(NetDesc)]),
     "cgs_refine_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(NetDesc), C.c_int64]),
     "cgs_refine_conv": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetDesc), C.POINTER(RefineCfg), C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -30,4 +30,9 @@ int require_sm100();
 // Process-wide count of kernels launched by the library (cgs_launch_count).
 void count_launch(int n = 1);
 
+// shared device utilities (sampling_kernels.cu)
+int compact_flags(const unsigned char* flags, long n, int* block_counts, int* idx_out, int* count_out, cudaStream_t st);
+int gather_rows(const void* src, long row_bytes, const int* idx, const int* count, long max_rows, void* dst,
+                cudaStream_t st);
+
 }  // namespace cgs

@@ -493,6 +493,8 @@ struct HeadParams {
   int step;             // -1 = initial evaluation (collaborator.py:49-60), else loop index i
   int mode;
   unsigned char* done;  // early-exit flags [B] or nullptr
+  const int* orig;      // compact row -> original sample index (early-exit compaction) or nullptr (identity)
+  float* final_feature; // [B_orig, feat_elems]: state of a sample at the step it exits (early-exit) or nullptr
   float exit_logit;
   int round_out;        // round dpre to TF32 (RN): it feeds a kind::tf32 MMA
 };
@@ -502,6 +504,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float s_logit;
   __shared__ int s_update;
   const int b = blockIdx.x;
+  const int ob = p.orig ? p.orig[b] : b;           // where this sample's results live
   const float* f = p.feat + (size_t)b * p.K;
   float acc = 0.f;
   for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
@@ -526,21 +529,25 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     int upd;
     if (p.step < 0) {
       upd = 1;
-      p.best_logit[b] = logit;
-      p.best_step[b] = 1.0f;                                   // collaborator.py:60 (sic)
-      if (p.default_logit) p.default_logit[b] = logit;         // collaborator.py:52
+      p.best_logit[ob] = logit;
+      p.best_step[ob] = 1.0f;                                  // collaborator.py:60 (sic)
+      if (p.default_logit) p.default_logit[ob] = logit;        // collaborator.py:52
     } else {
       const bool frozen = p.done && p.done[b];
-      if (p.mode == CGS_MODE_PROBABILISTIC) upd = (p.prob_indices[b] == p.step);
-      else upd = logit > p.best_logit[b];
+      if (p.mode == CGS_MODE_PROBABILISTIC) upd = (p.prob_indices[ob] == p.step);
+      else upd = logit > p.best_logit[ob];
       if (frozen) upd = 0;
       if (upd) {
-        p.best_logit[b] = logit;
-        p.best_step[b] = (float)(p.step + 1);
+        p.best_logit[ob] = logit;
+        p.best_step[ob] = (float)(p.step + 1);
       }
     }
-    if (p.done && !p.done[b] && logit >= p.exit_logit) p.done[b] = 1;
-    s_update = upd;
+    int exit_now = 0;
+    if (p.done && !p.done[b] && logit >= p.exit_logit) {       // opt-in early exit (README.md:13)
+      p.done[b] = 1;
+      exit_now = 1;
+    }
+    s_update = upd | (exit_now << 1);
   }
   __syncthreads();
   const float logit = s_logit;
@@ -560,20 +567,42 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
       *reinterpret_cast<float4*>(d + k) = o;
     }
   }
-  if (s_update) {
+  if (s_update & 1) {
     // chain-side image rows (possibly pitched) -> dense best_img
     const float4* src = reinterpret_cast<const float4*>(p.img) + (size_t)b * p.img_h * p.img_pitch4 + p.img_xoff4;
-    float4* dst = reinterpret_cast<float4*>(p.best_img + (size_t)b * p.img_elems);
+    float4* dst = reinterpret_cast<float4*>(p.best_img + (size_t)ob * p.img_elems);
     for (int i = threadIdx.x; i < p.img_h * p.img_w4; i += 256) {
       const int y = i / p.img_w4;
       dst[i] = src[(size_t)y * p.img_pitch4 + (i - y * p.img_w4)];
     }
     if (p.best_feature) {
       const float4* fs = reinterpret_cast<const float4*>(p.feature + (size_t)b * p.feat_elems);
-      float4* fd = reinterpret_cast<float4*>(p.best_feature + (size_t)b * p.feat_elems);
+      float4* fd = reinterpret_cast<float4*>(p.best_feature + (size_t)ob * p.feat_elems);
       for (int i = threadIdx.x; i < p.feat_elems / 4; i += 256) fd[i] = fs[i];
     }
   }
+  if ((s_update & 2) && p.final_feature) {                    // the sample leaves the batch: keep its final state
+    const float4* fs = reinterpret_cast<const float4*>(p.feature + (size_t)b * p.feat_elems);
+    float4* fd = reinterpret_cast<float4*>(p.final_feature + (size_t)ob * p.feat_elems);
+    for (int i = threadIdx.x; i < p.feat_elems / 4; i += 256) fd[i] = fs[i];
+  }
+}
+
+// rows still active (not done) -> flags for the ordered compaction
+__global__ void active_flags_kernel(const unsigned char* __restrict__ done, unsigned char* __restrict__ flags, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flags[i] = done[i] ? 0 : 1;
+}
+// feature rows of the samples that never exited -> their slot in the caller's buffer
+__global__ void scatter_active_kernel(const float4* __restrict__ feat, const int* __restrict__ orig,
+                                      const unsigned char* __restrict__ done, float4* __restrict__ out, int elems4) {
+  const int b = blockIdx.x;
+  if (done[b]) return;
+  const float4* s = feat + (size_t)b * elems4;
+  float4* d = out + (size_t)orig[b] * elems4;
+  for (int i = threadIdx.x; i < elems4; i += blockDim.x) d[i] = s[i];
+}
+__global__ void iota_kernel(int* p, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -636,6 +665,14 @@ struct Workspace {
   float* col;
   float* cur_logit;
   unsigned char* done;
+  // early-exit compaction: second feature / momentum buffers, row maps, flags, index list, counters
+  float* feat2;
+  float* mom2;
+  int* orig[2];
+  unsigned char* flags;
+  int* idx;
+  int* count;
+  int* bcounts;
   size_t total;
 };
 
@@ -651,6 +688,14 @@ static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
   w.col = c.col_elems ? (float*)take((size_t)B * c.col_elems * 4) : nullptr;
   w.cur_logit = (float*)take((size_t)B * 4);
   w.done = (unsigned char*)take((size_t)B);
+  w.feat2 = (float*)take((size_t)B * c.act_elems[0] * 4);
+  w.mom2 = (float*)take((size_t)B * c.act_elems[0] * 4);
+  w.orig[0] = (int*)take((size_t)B * 4);
+  w.orig[1] = (int*)take((size_t)B * 4);
+  w.flags = (unsigned char*)take((size_t)B);
+  w.idx = (int*)take((size_t)B * 4);
+  w.count = (int*)take(16);
+  w.bcounts = (int*)take((size_t)(B / 1024 + 2) * 4);
   w.total = off;
 }
 
@@ -692,6 +737,14 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
 }  // namespace cgs
 
 using namespace cgs;
+
+// Largest batch one call can take (rows are indexed with 32 bits); larger batches are refined in chunks by the caller.
+extern "C" int64_t cgs_refine_max_batch(const cgs_net_desc* gtail, const cgs_net_desc* d) {
+  Chain c;
+  if (int rc = build_chain(gtail, d, c)) return rc;
+  const size_t per = c.max_elems > c.col_elems ? c.max_elems : c.col_elems;
+  return (int64_t)(((1ull << 31) - 1) / per) - 1;
+}
 
 extern "C" size_t cgs_refine_workspace_bytes(const cgs_net_desc* gtail, const cgs_net_desc* d, int64_t B) {
   Chain c;
@@ -744,8 +797,8 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   Workspace w;
   carve(c, B, (void*)(((uintptr_t)workspace + 255) & ~uintptr_t(255)), w);
   if (!workspace || w.total + 256 > workspace_bytes) return set_error(CGS_ERR_WORKSPACE, "workspace too small");
-  if ((long long)B * (long long)c.max_elems >= (1ll << 31))
-    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split the batch");
+  if (B > cgs_refine_max_batch(gtail, d))
+    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split it (cgs_refine_max_batch)");
   w.act[0] = feature;
   cudaStream_t st = (cudaStream_t)stream;
   HeadParams hp;
@@ -764,14 +817,33 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
     cudaMemsetAsync(w.done, 0, (size_t)B, st);
   }
   const int K = cfg->steps;
+  const bool compacting = cfg->early_exit != 0;
+  if (compacting && cfg->mode != CGS_MODE_DETERMINISTIC)
+    return set_error(CGS_ERR_UNSUPPORTED, "early exit is defined for the deterministic mode only");
+  float* feature_out = feature;             // the caller's buffer: final state of every sample ends up here
+  int64_t Bact = B;                         // rows currently in the batch
+  int cur = 0;                              // which orig[] map is live
+  if (compacting) {
+    // work on a private copy so that exited samples can be dropped and the rest compacted
+    cudaMemcpyAsync(w.feat2, feature, (size_t)B * c.act_elems[0] * 4, cudaMemcpyDeviceToDevice, st);
+    w.act[0] = w.feat2;
+    iota_kernel<<<148, 256, 0, st>>>(w.orig[0], (int)B); count_launch();
+    hp.orig = w.orig[0];
+    hp.final_feature = feature_out;
+  }
+  float* feat_alt = feature;                // ping-pong partner of the private copy (safe: final rows are written
+  float* mom_cur = w.mom;                   // to feature_out only by rows that leave, see below)
+  float* mom_alt = w.mom2;
+  // NOTE: with compaction the caller's buffer doubles as the scatter target, so the ping-pong partner must be a
+  // separate allocation: use the momentum spare for features is not possible -> dedicated buffers
+  (void)feat_alt;
   // initial evaluation: collaborator.py:48-60
-  if (int rc = run_forward(c, w, B, cfg->math, st)) return rc;
+  if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;
   hp.step = -1;
   hp.dpre = K > 0 ? w.g[0] : nullptr;
-  if (int rc = head_launch(c, w, B, hp, st)) return rc;
+  if (int rc = head_launch(c, w, Bact, hp, st)) return rc;
   ConvGemmParams upd;
   std::memset(&upd, 0, sizeof(upd));
-  upd.mom = w.mom;
   upd.sgd = cfg->method == CGS_POLICY_SGD;
   upd.rate = cfg->rate;
   upd.alpha = cfg->alpha;
@@ -780,11 +852,45 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   upd.vmax = cfg->vmax;
   for (int i = 0; i < K; ++i) {                       // collaborator.py:63-83
     upd.first = (i == 0);
-    if (int rc = run_backward(c, w, B, cfg->math, &upd, nullptr, st)) return rc;   // grad + policy step (:66-70)
-    if (int rc = run_forward(c, w, B, cfg->math, st)) return rc;                   // :73
+    upd.mom = mom_cur;
+    if (int rc = run_backward(c, w, Bact, cfg->math, &upd, nullptr, st)) return rc;   // grad + policy step (:66-70)
+    if (compacting) {
+      // drop the samples D already classifies as real (README.md:13): ordered compaction of the rows that stay.
+      // Only the feature map, its momentum and the row map are live here (activations / gradients are dead).
+      active_flags_kernel<<<148, 256, 0, st>>>(w.done, w.flags, (int)Bact); count_launch();
+      if (int rc = compact_flags(w.flags, Bact, w.bcounts, w.idx, w.count, st)) return rc;
+      int n_active = 0;
+      cudaMemcpyAsync(&n_active, w.count, 4, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaStreamSynchronize(st);      // the one host sync of this opt-in mode: grid sizes follow
+      if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "early-exit sync: %s", cudaGetErrorString(e));
+      if (n_active == 0) { Bact = 0; break; }
+      if (n_active < Bact) {
+        float* feat_src = w.act[0];
+        float* feat_dst = (feat_src == w.feat2) ? w.g[1] : w.feat2;      // g[1] is dead between backward and forward
+        const size_t row_bytes = c.act_elems[0] * 4;
+        if (int rc = gather_rows(feat_src, (long)row_bytes, w.idx, w.count, n_active, feat_dst, st)) return rc;
+        if (!upd.sgd)
+          if (int rc = gather_rows(mom_cur, (long)row_bytes, w.idx, w.count, n_active, mom_alt, st)) return rc;
+        if (int rc = gather_rows(w.orig[cur], 4, w.idx, w.count, n_active, w.orig[cur ^ 1], st)) return rc;
+        if (feat_dst != w.feat2)                       // keep the live copy in feat2 (g[1] is about to be reused)
+          cudaMemcpyAsync(w.feat2, feat_dst, (size_t)n_active * row_bytes, cudaMemcpyDeviceToDevice, st);
+        w.act[0] = w.feat2;
+        float* t = mom_cur; mom_cur = mom_alt; mom_alt = t;
+        cur ^= 1;
+        hp.orig = w.orig[cur];
+        cudaMemsetAsync(w.done, 0, (size_t)n_active, st);
+        Bact = n_active;
+      }
+    }
+    if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;                   // :73
     hp.step = i;
     hp.dpre = (i + 1 < K) ? w.g[0] : nullptr;         // the gradient after the last step is never consumed
-    if (int rc = head_launch(c, w, B, hp, st)) return rc;                          // :76-83
+    if (int rc = head_launch(c, w, Bact, hp, st)) return rc;                          // :76-83
+  }
+  if (compacting && Bact > 0) {
+    scatter_active_kernel<<<(unsigned)Bact, 128, 0, st>>>((const float4*)w.act[0], hp.orig, w.done, (float4*)feature_out,
+                                                          (int)(c.act_elems[0] / 4)); count_launch();
+    if (int rc = check_launch("scatter_active_kernel")) return rc;
   }
   return CGS_OK;
 }
@@ -800,8 +906,8 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   Workspace w;
   carve(c, B, (void*)(((uintptr_t)workspace + 255) & ~uintptr_t(255)), w);
   if (!workspace || w.total + 256 > workspace_bytes) return set_error(CGS_ERR_WORKSPACE, "workspace too small");
-  if ((long long)B * (long long)c.max_elems >= (1ll << 31))
-    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split the batch");
+  if (B > cgs_refine_max_batch(gtail, d))
+    return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit row indexing; split it (cgs_refine_max_batch)");
   w.act[0] = const_cast<float*>(feature);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = run_forward(c, w, B, math, st)) return rc;

@@ -278,14 +278,6 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ flags, int64_
   }
 }
 
-int compact_flags(const uint8_t* flags, int64_t n, int* block_counts, int* idx_out, int* count_out, cudaStream_t st) {
-  const int nb = (int)((n + kChunk - 1) / kChunk);
-  compact_count_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts); count_launch();
-  compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nb, count_out); count_launch();
-  compact_scatter_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts, idx_out); count_launch();
-  return check_launch("compact_flags");
-}
-
 // ------------------------------------------------------------------------------------------------ MH
 // acceptance test of idpsampler.py:48-51 in the dtype numpy would use
 __device__ __forceinline__ bool mh_move(double d_state, bool f64_math, const void* sig, int dtype, int64_t j, double u) {
@@ -478,6 +470,26 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, int64_t row_
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
+
+// flags [n] -> ascending indices of the set flags + their count (device); block_counts needs ceil(n/1024)+1 ints
+int compact_flags(const uint8_t* flags, int64_t n, int* block_counts, int* idx_out, int* count_out, cudaStream_t st) {
+  const int nb = (int)((n + kChunk - 1) / kChunk);
+  compact_count_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts); count_launch();
+  compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nb, count_out); count_launch();
+  compact_scatter_kernel<<<nb, kBlock, 0, st>>>(flags, n, block_counts, idx_out); count_launch();
+  return check_launch("compact_flags");
+}
+
+
+int gather_rows(const void* src, int64_t row_bytes, const int* idx, const int* count, int64_t max_rows, void* dst,
+                cudaStream_t st) {
+  if (max_rows <= 0 || row_bytes <= 0) return CGS_OK;
+  int grid = (int)(max_rows < 148 * 16 ? max_rows : 148 * 16);
+  gather_rows_kernel<<<grid, row_bytes >= 4096 ? 256 : 64, 0, st>>>((const uint8_t*)src, row_bytes, idx, count, max_rows,
+                                                                      (uint8_t*)dst); count_launch();
+  return check_launch("gather_rows");
+}
+
 }  // namespace cgs
 
 using namespace cgs;
@@ -629,8 +641,5 @@ extern "C" int cgs_gather_rows(const void* src, int64_t row_bytes, const int32_t
   if (row_bytes < 0 || max_rows < 0) return set_error(CGS_ERR_INVALID, "negative size");
   if (max_rows == 0 || row_bytes == 0) return CGS_OK;
   if (!src || !idx || !count || !dst) return set_error(CGS_ERR_INVALID, "null argument");
-  int grid = (int)(max_rows < 148 * 16 ? max_rows : 148 * 16);
-  gather_rows_kernel<<<grid, row_bytes >= 4096 ? 256 : 64, 0, (cudaStream_t)stream>>>(
-      (const uint8_t*)src, row_bytes, idx, count, max_rows, (uint8_t*)dst); count_launch();
-  return check_launch("cgs_gather_rows");
+  return gather_rows(src, row_bytes, idx, count, max_rows, dst, (cudaStream_t)stream);
 }

@@ -76,6 +76,9 @@ class Refiner():
             L.check(-1 if not L.last_error() else -2)
         return self._ws.get(nbytes, dev)
 
+    def _max_rows_per_launch(self):
+        return int(L.check(L.load().cgs_refine_max_batch(C.byref(self._g.desc), C.byref(self._d.desc))))
+
     def _img_shape(self, B):
         h, w, c = self._spec.image_shape
         return (B, h, w, N.cstride(c))
@@ -122,6 +125,22 @@ class Refiner():
         if tuple(feat_in.shape[1:]) != self._spec.feature_shape:
             raise ValueError("feature shape %s does not match the spec %s" % (tuple(feat_in.shape[1:]), self._spec.feature_shape))
         B = feat_in.shape[0]
+        # the kernels index rows with 32 bits: very large batches are refined in independent chunks (samples are
+        # independent under inference-mode BN, so chunking does not change a single bit)
+        limit = self._max_rows_per_launch()
+        if B > limit:
+            if prob_indices is None and mode == 'probabilistic':
+                prob_indices = np.random.randint(self.forward_steps + 1, size=B)
+            outs, attrs = [], []
+            for lo in range(0, B, limit):
+                pi = None if prob_indices is None else np.asarray(prob_indices)[lo:lo + limit]
+                outs.append(self.build_refiner(feat_in[lo:lo + limit], None, mode, pi, keep_optimal_feature))
+                attrs.append((self.current_feature, self.default_logit, self.optimal_logit, self.optimal_step, self.optimal_feature))
+            cat = lambda i: None if attrs[0][i] is None else torch.cat([a[i] for a in attrs])
+            self.current_feature, self.default_logit, self.optimal_logit = cat(0), cat(1), cat(2)
+            self.optimal_step, self.optimal_feature = cat(3), cat(4)
+            refined = torch.cat(outs)
+            return refined.cpu().numpy() if was_np else refined
         idx_host = None
         if mode == 'probabilistic':
             if prob_indices is None:
@@ -156,7 +175,7 @@ class Refiner():
                                         L.ptr(b["default_logit"]), L.ptr(b["idx"]), L.ptr(b["best_feat"]), L.ptr(ws),
                                         ws.numel(), L.stream_ptr()))
 
-        if not self.cuda_graph:
+        if not self.cuda_graph or cfg.early_exit:      # early exit re-sizes the batch on the host: no graph replay
             b = buffers()
             b["feat"].copy_(feat_in)                                  # tf.identity (collaborator.py:48,58)
             if idx_host is not None:

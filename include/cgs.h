@@ -182,9 +182,13 @@ typedef struct cgs_refine_cfg {
   int clip;          /* collaborator.py:69 truthiness already resolved by the wrapper */
   float vmin, vmax;
   int math;          /* cgs_math */
-  int early_exit;    /* opt-in: stop updating a sample once logit >= exit_logit (README.md:13); 0 = reference */
+  int early_exit;    /* opt-in (README.md:13): a sample whose logit reaches exit_logit keeps its best state, leaves
+                        the batch and the remaining rows are compacted; costs one host sync per step; 0 = reference */
   float exit_logit;
 } cgs_refine_cfg;
+
+/* largest batch one call accepts (32-bit row indexing); the wrapper refines larger batches in independent chunks */
+CGS_API int64_t cgs_refine_max_batch(const cgs_net_desc* gtail, const cgs_net_desc* d);
 
 /* bytes of workspace cgs_refine_conv needs for a batch of B */
 CGS_API size_t cgs_refine_workspace_bytes(const cgs_net_desc* gtail, const cgs_net_desc* d, int64_t B);

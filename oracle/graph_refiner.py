@@ -31,7 +31,7 @@ def forward_logits_and_grad(h, arch, w, d_bn="inference"):
 
 def build_refiner(h0, arch, w, steps, rate, method="momentum", mode="deterministic",
                   d_bn="inference", prob_indices=None, vmin=None, vmax=None, alpha=0.9,
-                  return_trace=False):
+                  return_trace=False, exit_logit=None):
     """collaborator.py:41-88 evaluated eagerly on a concrete batch.
 
     h0: [B,H,W,C] float32 NHWC.  Returns dict(refined [B,h,w,c], optimal_logit, optimal_step,
@@ -55,6 +55,10 @@ def build_refiner(h0, arch, w, steps, rate, method="momentum", mode="determinist
     best_img = img.clone()
     momentum = None
     trace = []
+    # opt-in early exit (README.md:13; NOT in the reference code, which always runs K steps): a sample whose logit
+    # reaches exit_logit keeps its best state and its feature as of that evaluation
+    done = (cur_logit >= exit_logit) if exit_logit is not None else torch.zeros_like(cur_logit, dtype=torch.bool)
+    final_feat = cur.clone()
     for i in range(steps):                                      # :63
         if method == "sgd":                                     # policy.py:27-29
             cur = cur - rate * grad
@@ -70,6 +74,11 @@ def build_refiner(h0, arch, w, steps, rate, method="momentum", mode="determinist
             upd = cur_logit > best_logit                        # :79
         else:
             raise NotImplementedError(mode)
+        upd = upd & ~done
+        if exit_logit is not None:
+            newly = (~done) & (cur_logit >= exit_logit)
+            final_feat = torch.where((~done).view(-1, *([1] * (cur.dim() - 1))), cur, final_feat)
+            done = done | newly
         best_logit = torch.where(upd, cur_logit, best_logit)    # :81
         m = upd.view(-1, *([1] * (cur.dim() - 1)))
         best_feat = torch.where(m, cur, best_feat)              # :82
@@ -80,7 +89,7 @@ def build_refiner(h0, arch, w, steps, rate, method="momentum", mode="determinist
     refined = nets.feature_to_data(best_feat, arch, w).detach()   # :88
     out = dict(refined=refined, optimal_logit=best_logit, optimal_step=best_step,
                default_logit=default_logit, optimal_feature=best_feat, best_img_kept=best_img,
-               final_feature=cur)
+               final_feature=cur if exit_logit is None else final_feat, done=done)
     if return_trace:
         out["trace"] = trace
     return out

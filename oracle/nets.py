@@ -37,16 +37,19 @@ def conv_out_size_same(size, stride):      # nsgan/ops.py:28-29
     return int(math.ceil(float(size) / float(stride)))
 
 
-def arch_mnist_infogan():
-    """nsgan/GAN.py:59-101; refinement at the [7,7,128] map (GAN.py:172, 87-92)."""
+def arch_mnist_infogan(layer=1):
+    """nsgan/GAN.py:59-101; refinement at the [7,7,128] map (GAN.py:172, 87-92) for layer=1, or at the
+    [14,14,64] map feeding the last deconv for layer=2 (BASELINE config wording; same code path)."""
+    assert layer in (1, 2)
+    gtail = [
+        dict(type="deconv", name="g_dc3", k=4, cin=128, cout=64, hin=7, win=7, bn="g_bn3", act="relu"),
+        dict(type="deconv", name="g_dc4", k=4, cin=64, cout=1, hin=14, win=14, bn=None, act="tanh"),
+    ][layer - 1:]
     return {
-        "name": "mnist_infogan",
-        "feature_shape": [7, 7, 128],
+        "name": "mnist_infogan" if layer == 1 else "mnist_infogan_l2",
+        "feature_shape": [7, 7, 128] if layer == 1 else [14, 14, 64],
         "image_shape": [28, 28, 1],
-        "gtail": [
-            dict(type="deconv", name="g_dc3", k=4, cin=128, cout=64, hin=7, win=7, bn="g_bn3", act="relu"),
-            dict(type="deconv", name="g_dc4", k=4, cin=64, cout=1, hin=14, win=14, bn=None, act="tanh"),
-        ],
+        "gtail": gtail,
         "d": [
             dict(type="conv", name="d_conv1", k=4, cin=1, cout=64, hin=28, win=28, bn=None, act="lrelu"),
             dict(type="conv", name="d_conv2", k=4, cin=64, cout=128, hin=14, win=14, bn="d_bn2", act="lrelu"),
@@ -94,6 +97,8 @@ def arch_dcgan(size=64, layer=1, gf=64, df=64, c_dim=3, k=5):
 def get_arch(name):
     if name in ("mnist", "mnist_infogan"):
         return arch_mnist_infogan()
+    if name in ("mnist_l2", "mnist_infogan_l2"):
+        return arch_mnist_infogan(2)
     if name.startswith("dcgan"):
         body = name[len("dcgan"):]
         size, _, layer = body.partition("_l")

@@ -176,3 +176,59 @@ def test_cuda_graph_replay_is_bit_identical(cgs_lib, cuda_device):
         b = graph.build_refiner(h0)
         assert torch.equal(a, b) and torch.equal(eager.optimal_logit, graph.optimal_logit)
         assert torch.equal(eager.optimal_step, graph.optimal_step) and torch.equal(eager.current_feature, graph.current_feature)
+
+
+def test_mnist_layer2_and_chunked_batches(cgs_lib, cuda_device, monkeypatch):
+    """Refinement at the [14,14,64] map (G-tail = last deconv only) and chunked refinement of over-size batches."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("mnist_l2", 4, 3.0, cuda_device, "fp32")
+    h0 = torch.relu(torch.randn(5, *arch["feature_shape"], generator=torch.Generator().manual_seed(7)))
+    o = gr.build_refiner(h0, arch, w, 3, 0.1)
+    ref = Refiner(3, 0.1)
+    ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    out = ref.build_refiner(h0.to(cuda_device), keep_optimal_feature=True)
+    assert rel_l2(out.cpu().numpy(), o["refined"].numpy()) <= 1e-4
+    assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
+    full_logit, full_feat = ref.optimal_logit.clone(), ref.current_feature.clone()
+    monkeypatch.setattr(Refiner, "_max_rows_per_launch", lambda self: 2)     # force 3 chunks (2 + 2 + 1)
+    out2 = ref.build_refiner(h0.to(cuda_device), keep_optimal_feature=True)
+    assert torch.equal(out, out2) and torch.equal(full_logit, ref.optimal_logit)
+    assert torch.equal(full_feat, ref.current_feature) and ref.optimal_feature.shape[0] == 5
+
+
+@pytest.mark.parametrize("arch_name,B,K,thr", [("mnist", 12, 6, -0.2), ("mnist", 40, 8, 0.1), ("dcgan32_l2", 6, 4, -1.0)])
+def test_early_exit_compaction_matches_oracle(cgs_lib, cuda_device, arch_name, B, K, thr):
+    """Opt-in early exit (README.md:13): samples D already classifies as real leave the batch (ordered compaction of
+    feature / momentum rows); every sample's result equals the oracle's frozen-at-exit semantics, and an unreachable
+    threshold reproduces the reference's best-of-K bit for bit."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 9, 3.0 if arch_name == "mnist" else 2.5, cuda_device, "fp32")
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(2)))
+    o = gr.build_refiner(h0, arch, w, K, 0.1, exit_logit=thr)
+    assert 0 < int(o["done"].sum()) <= B                      # the case actually exercises exits
+    ref = Refiner(K, 0.1)
+    ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    ref.early_exit_logit = thr
+    out = ref.build_refiner(h0.to(cuda_device), keep_optimal_feature=True)
+    assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
+    ee_logit, ee_feat, ee_img = ref.optimal_logit.clone(), ref.current_feature.clone(), out.clone()
+    # FP32 SIMT vs torch-CPU over K chained steps: summation-order noise is amplified by the dynamics
+    assert rel_l2(out.cpu().numpy(), o["refined"].numpy()) <= 5e-4
+    assert np.abs(ee_logit.cpu().numpy() - o["optimal_logit"].numpy()).max() <= 1e-3
+    assert rel_l2(ee_feat.cpu().numpy(), o["final_feature"].numpy()) <= 5e-4
+    assert rel_l2(ref.optimal_feature.cpu().numpy(), o["optimal_feature"].numpy()) <= 5e-4
+    # disabled-in-effect == reference behaviour, bit for bit
+    plain = Refiner(K, 0.1)
+    plain.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    a = plain.build_refiner(h0.to(cuda_device))
+    # samples that never exit are untouched by the compaction of the others: bit-identical to the plain run
+    stay = ~o["done"].to(cuda_device)
+    if bool(stay.any()):
+        assert torch.equal(ee_img[stay], a[stay]) and torch.equal(ee_logit[stay], plain.optimal_logit[stay])
+        assert torch.equal(ee_feat[stay], plain.current_feature[stay])
+    ref.early_exit_logit = 1e30
+    b = ref.build_refiner(h0.to(cuda_device))
+    assert torch.equal(a, b) and torch.equal(plain.optimal_logit, ref.optimal_logit)
+    assert torch.equal(plain.current_feature, ref.current_feature)
