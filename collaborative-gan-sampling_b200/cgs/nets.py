@@ -41,6 +41,14 @@ def arch_mnist_infogan(layer=1):
         "name": "mnist_infogan" if layer == 1 else "mnist_infogan_l2",
         "feature_shape": [7, 7, 128] if layer == 1 else [14, 14, 64],
         "image_shape": [28, 28, 1],
+        # proposal head = nsgan/GAN.py:87-92 input_to_feature (BN inference); only used to produce proposals from z
+        "z_dim": 62,
+        "head": [
+            dict(type="fc", name="g_fc1", cin=62, cout=1024, bn="g_bn1", act="relu"),
+            dict(type="fc", name="g_fc2", cin=1024, cout=6272, bn="g_bn2", act="relu"),
+        ] + ([dict(type="deconv", name="g_dc3", k=4, cin=128, cout=64, hin=7, win=7, bn="g_bn3", act="relu")]
+             if layer == 2 else []),
+        "head_reshape": [7, 7, 128],
         "gtail": gtail,
         "d": [
             dict(type="conv", name="d_conv1", k=4, cin=1, cout=64, hin=28, win=28, bn=None, act="lrelu"),
@@ -71,9 +79,16 @@ def arch_dcgan(size=64, layer=1, gf=64, df=64, c_dim=3, k=5):
     d = [dict(type="conv", name="d_h%d_conv" % i, k=k, cin=dch[i], cout=dch[i + 1], hin=dsz[i], win=dsz[i],
               bn=None if i == 0 else "d_bn%d" % i, act="lrelu") for i in range(4)]
     d.append(dict(type="fc", name="d_h4_lin", cin=sizes[4] * sizes[4] * df * 8, cout=1, bn=None, act="none"))
+    # proposal head (upstream DCGAN generator up to the refined map): linear -> reshape -> bn0 -> relu [-> deconvs]
+    head = [dict(type="fc", name="g_h0_lin", cin=100, cout=gsz[0] * gsz[0] * gch[0], bn="g_bn0", bn_channels=gch[0],
+                 act="relu")]
+    for i in range(layer - 1):
+        head.append(dict(type="deconv", name="g_h%d" % (i + 1), k=k, cin=gch[i], cout=gch[i + 1], hin=gsz[i], win=gsz[i],
+                         bn="g_bn%d" % (i + 1), act="relu"))
     return {"name": "dcgan%d_l%d" % (size, layer),
             "feature_shape": [gsz[layer - 1], gsz[layer - 1], gch[layer - 1]],
-            "image_shape": [size, size, c_dim], "gtail": gtail, "d": d}
+            "image_shape": [size, size, c_dim], "z_dim": 100, "head": head, "head_reshape": [gsz[0], gsz[0], gch[0]],
+            "gtail": gtail, "d": d}
 
 
 def get_arch(name):
@@ -106,6 +121,9 @@ def fold_layer(layer, scope, weights):
         q = "%s/%s/" % (scope, layer["bn"])
         s = _as_t(weights[q + "gamma"]).double() / torch.sqrt(_as_t(weights[q + "moving_variance"]).double() + BN_EPS)
         t = _as_t(weights[q + "beta"]).double() - _as_t(weights[q + "moving_mean"]).double() * s
+        if layer.get("bn_channels"):            # BN applied after an NHWC reshape of a linear output: tile per channel
+            rep = layer["cout"] // layer["bn_channels"]
+            s, t = s.repeat(rep), t.repeat(rep)
         if layer["type"] == "conv":
             w = (w.double() * s.view(1, 1, 1, -1)).float()
         elif layer["type"] == "deconv":
@@ -116,11 +134,16 @@ def fold_layer(layer, scope, weights):
     return w, b
 
 
+def _padded_cin(layer):
+    """fc inputs are padded with zeros to a multiple of 32 (one K atom), e.g. z_dim 62 -> 64, 100 -> 128."""
+    return (layer["cin"] + 31) // 32 * 32 if layer["type"] == "fc" else layer["cin"]
+
+
 def _layer_desc(layer):
     d = L.LayerDesc()
     d.type = L.LAYER_IDS[layer["type"]]
     d.k = layer.get("k", 1)
-    d.cin, d.cout = layer["cin"], layer["cout"]
+    d.cin, d.cout = _padded_cin(layer), layer["cout"]
     d.hin, d.win = layer.get("hin", 1), layer.get("win", 1)
     d.act = L.ACT_IDS[layer["act"]]
     return d
@@ -140,7 +163,9 @@ def pack_map(layer, backward):
 
 def pack_layer(layer, w, b):
     """Folded TF-layout weights -> (w_fwd [cout, Kf], w_bwd [cin, Kb] or None, bias [cstride(cout)])."""
-    cin, cout = layer["cin"], layer["cout"]
+    cin, cout = _padded_cin(layer), layer["cout"]
+    if cin != layer["cin"]:                    # zero rows for the padded fc inputs
+        w = torch.cat([w, torch.zeros(cin - layer["cin"], cout)], dim=0)
     bias = torch.zeros(cstride(cout))
     bias[:cout] = b
     if layer["type"] == "fc" and cout == 1:
@@ -273,3 +298,42 @@ def loss_refine(logits=None):
 
 
 loss_refine.is_bce_with_ones = True
+
+
+class ProposalHead:
+    """z -> refined activation map on the device: ``input_to_feature`` of nsgan/GAN.py:87-92 (fc+BN+relu x2) or the
+    DCGAN generator up to the refined layer (linear, reshape, bn0, relu[, deconvs]); BN in inference mode, folded.
+    Runs the same gathered-GEMM kernel as the refinement loop."""
+
+    def __init__(self, arch, weights, device="cuda", math="tf32"):
+        self.arch = arch
+        self.math = math
+        self.device = torch.device(device)
+        self.net = PackedNet(arch["head"], "generator", weights, self.device, math)
+        self._ws = None
+
+    def __call__(self, z):
+        import ctypes as C
+        lib = L.load()
+        zt = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32))
+        x = zt.to(self.device, torch.float32)
+        B = x.shape[0]
+        for i, layer in enumerate(self.net.layers):
+            d = self.net.layer_desc(i)
+            if layer["type"] == "fc":
+                x = x.reshape(B, -1)
+                if x.shape[1] != d.cin:
+                    x = torch.nn.functional.pad(x, (0, d.cin - x.shape[1]))
+                y = torch.empty(B, cstride(layer["cout"]), dtype=torch.float32, device=self.device)
+            else:
+                if x.dim() == 2:
+                    x = x.reshape(B, *self.arch["head_reshape"])
+                y = torch.empty(B, layer["hin"] * 2, layer["win"] * 2, cstride(layer["cout"]), dtype=torch.float32,
+                                device=self.device)
+            nbytes = int(lib.cgs_layer_workspace_bytes(C.byref(d), B))
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            L.check(lib.cgs_layer_forward(C.byref(d), L.MATH_IDS[self.math], B, L.ptr(x.contiguous()), L.ptr(y),
+                                          L.ptr(self._ws), self._ws.numel(), L.stream_ptr()))
+            x = y
+        return x.reshape(B, *self.arch["feature_shape"])

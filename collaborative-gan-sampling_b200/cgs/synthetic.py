@@ -24,9 +24,11 @@ def init_weights(arch, seed=2019, gain=1.0, dtype=np.float32):
             bad = np.abs(x) > 2
         return (x * std).astype(dtype)
 
-    for scope, layers in (("generator", arch["gtail"]), ("discriminator", arch["d"])):
+    for scope, layers in (("generator", arch["gtail"]), ("discriminator", arch["d"]), ("generator", arch.get("head", []))):
         for L in layers:
             p = "%s/%s/" % (scope, L["name"])
+            if (p + "w") in w or (p + "Matrix") in w:
+                continue
             if L["type"] == "conv":
                 w[p + "w"] = tn((L["k"], L["k"], L["cin"], L["cout"]), 0.02)
                 w[p + "biases"] = (0.01 * rng.standard_normal(L["cout"])).astype(dtype)
@@ -38,7 +40,7 @@ def init_weights(arch, seed=2019, gain=1.0, dtype=np.float32):
                 w[p + "bias"] = (0.01 * rng.standard_normal(L["cout"])).astype(dtype)
             if L["bn"]:
                 q = "%s/%s/" % (scope, L["bn"])
-                c = L["cout"]
+                c = L.get("bn_channels") or L["cout"]
                 w[q + "gamma"] = (1.0 + 0.1 * rng.standard_normal(c)).astype(dtype)
                 w[q + "beta"] = (0.05 * rng.standard_normal(c)).astype(dtype)
                 w[q + "moving_mean"] = (0.1 * rng.standard_normal(c)).astype(dtype)

@@ -49,6 +49,14 @@ def arch_mnist_infogan(layer=1):
         "name": "mnist_infogan" if layer == 1 else "mnist_infogan_l2",
         "feature_shape": [7, 7, 128] if layer == 1 else [14, 14, 64],
         "image_shape": [28, 28, 1],
+        # proposal head = nsgan/GAN.py:87-92 input_to_feature (BN inference); only used to produce proposals from z
+        "z_dim": 62,
+        "head": [
+            dict(type="fc", name="g_fc1", cin=62, cout=1024, bn="g_bn1", act="relu"),
+            dict(type="fc", name="g_fc2", cin=1024, cout=6272, bn="g_bn2", act="relu"),
+        ] + ([dict(type="deconv", name="g_dc3", k=4, cin=128, cout=64, hin=7, win=7, bn="g_bn3", act="relu")]
+             if layer == 2 else []),
+        "head_reshape": [7, 7, 128],
         "gtail": gtail,
         "d": [
             dict(type="conv", name="d_conv1", k=4, cin=1, cout=64, hin=28, win=28, bn=None, act="lrelu"),
@@ -85,10 +93,16 @@ def arch_dcgan(size=64, layer=1, gf=64, df=64, c_dim=3, k=5):
         d.append(dict(type="conv", name="d_h%d_conv" % i, k=k, cin=dch[i], cout=dch[i + 1],
                       hin=dsz[i], win=dsz[i], bn=None if i == 0 else "d_bn%d" % i, act="lrelu"))
     d.append(dict(type="fc", name="d_h4_lin", cin=s16 * s16 * df * 8, cout=1, bn=None, act="none"))
+    head = [dict(type="fc", name="g_h0_lin", cin=100, cout=gsz[0] * gsz[0] * gch[0], bn="g_bn0", bn_channels=gch[0],
+                 act="relu")]
+    for i in range(layer - 1):
+        head.append(dict(type="deconv", name="g_h%d" % (i + 1), k=k, cin=gch[i], cout=gch[i + 1], hin=gsz[i], win=gsz[i],
+                         bn="g_bn%d" % (i + 1), act="relu"))
     return {
         "name": "dcgan%d_l%d" % (size, layer),
         "feature_shape": [gsz[layer - 1], gsz[layer - 1], gch[layer - 1]],
         "image_shape": [size, size, c_dim],
+        "z_dim": 100, "head": head, "head_reshape": [gsz[0], gsz[0], gch[0]],
         "gtail": gtail,
         "d": d,
     }
@@ -130,9 +144,11 @@ def init_weights(arch, seed=2019, dtype=np.float32):
             bad = np.abs(x) > 2
         return (x * std).astype(dtype)
 
-    for scope, layers in (("generator", arch["gtail"]), ("discriminator", arch["d"])):
+    for scope, layers in (("generator", arch["gtail"]), ("discriminator", arch["d"]), ("generator", arch.get("head", []))):
         for L in layers:
             p = "%s/%s/" % (scope, L["name"])
+            if (p + "w") in w or (p + "Matrix") in w:
+                continue
             if L["type"] == "conv":
                 w[p + "w"] = tn((L["k"], L["k"], L["cin"], L["cout"]), 0.02)
                 w[p + "biases"] = (0.01 * rng.standard_normal(L["cout"])).astype(dtype)
@@ -144,7 +160,7 @@ def init_weights(arch, seed=2019, dtype=np.float32):
                 w[p + "bias"] = (0.01 * rng.standard_normal(L["cout"])).astype(dtype)
             if L["bn"]:
                 q = "%s/%s/" % (scope, L["bn"])
-                c = L["cout"]
+                c = L.get("bn_channels") or L["cout"]
                 w[q + "gamma"] = (1.0 + 0.1 * rng.standard_normal(c)).astype(dtype)
                 w[q + "beta"] = (0.05 * rng.standard_normal(c)).astype(dtype)
                 w[q + "moving_mean"] = (0.1 * rng.standard_normal(c)).astype(dtype)
@@ -260,11 +276,27 @@ def run_layers(x, layers, scope, w, bn_mode, collect=None):
             x = x @ _t(w, p + "Matrix") + _t(w, p + "bias")
         if L["bn"]:
             q = "%s/%s/" % (scope, L["bn"])
+            shp = x.shape
+            if L.get("bn_channels"):             # DCGAN: linear -> reshape [.., C] -> bn0 (per channel)
+                x = x.reshape(-1, L["bn_channels"])
             x = batch_norm(x, _t(w, q + "gamma"), _t(w, q + "beta"),
                            _t(w, q + "moving_mean"), _t(w, q + "moving_variance"), bn_mode)
+            x = x.reshape(shp)
         x = activation(x, L["act"])
         if collect is not None:
             collect.append(x)
+    return x
+
+
+def input_to_feature(z, arch, w):
+    """nsgan/GAN.py:87-92 (MNIST) / upstream DCGAN generator up to the refined map; BN in inference mode."""
+    x = torch.as_tensor(z, dtype=torch.float32)
+    fcs = [L for L in arch["head"] if L["type"] == "fc"]
+    rest = [L for L in arch["head"] if L["type"] != "fc"]
+    x = run_layers(x, fcs, "generator", w, "inference")
+    x = x.reshape(x.shape[0], *arch["head_reshape"])
+    if rest:
+        x = run_layers(x, rest, "generator", w, "inference")
     return x
 
 
