@@ -40,6 +40,7 @@ class Refiner():
         self.early_exit_logit = None      # opt-in (README.md:13); None = reference behaviour (best of K)
         self.cuda_graph = cuda_graph      # capture the K-step launch sequence once per batch shape and replay it
         self._graphs = {}
+        self.replayed_launches = 0        # kernels executed through graph replays (cgs_launch_count sees captures only)
         self._ws = R.Workspace()
         self.real_logits = None
         self.real_logits_mean = None
@@ -199,10 +200,12 @@ class Refiner():
                     launch(b, ws)                                     # warm-up outside capture (one-time attribute setup)
                 torch.cuda.current_stream(dev).wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
+                n0 = lib.cgs_launch_count()
                 with torch.cuda.graph(graph):
                     launch(b, ws)
-                ent = self._graphs[key] = (graph, b, ws)
-            graph, sb, _ = ent
+                ent = self._graphs[key] = (graph, b, ws, int(lib.cgs_launch_count() - n0))
+            graph, sb, _, n_kernels = ent
+            self.replayed_launches += n_kernels
             sb["feat"].copy_(feat_in)
             if idx_host is not None:
                 sb["idx"].copy_(torch.from_numpy(idx_host))
