@@ -292,6 +292,57 @@ def measure_extra(torch, name, dev, math, steps=2, warmup=1):
     return out
 
 
+def measure_2d(torch, dev, n=10000, steps_k=50, reps=5, cpu=True):
+    """BASELINE config 0: imbalanced-8-Gaussians-style 2-D MLP GAN, collaborative refine (ladam, K=50) + DRS + MH on
+    N=10 000 points (synthetic/main.py:299).  Device-timed; beside it the oracle port of refiner_cpu on the host."""
+    import types
+    import numpy as np
+    from cgs import synthetic as S
+    from sampling.idpsampler import IndependenceSampler
+    from sampling.refiner_cpu import MlpSpec, Refiner
+    from sampling.rejector import Rejector
+    ws = S.init_mlp2d(64, 6, seed=2019, gain=1.5)
+    mlp = MlpSpec(ws, dev)
+    rng = np.random.RandomState(0)
+    x0 = torch.from_numpy((rng.randn(n, 2) * 4).astype(np.float32)).to(dev)
+    real = (rng.randn(n, 2) * 3).astype(np.float32)
+    real_mean = float(np.mean(mlp.score(real)[0].cpu().numpy()))
+    ref = Refiner(types.SimpleNamespace(rollout_steps=steps_k, rollout_rate=0.1, rollout_method="ladam"))
+    ref.set_env(mlp, None, None)
+    rej = Rejector(rng="philox", seed=1)
+    mh = IndependenceSampler(T=20, rng="philox", seed=2)
+    mh.set_score_curr(np.float32(real_mean))
+    best = 1e9
+    for it in range(reps + 2):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        x = ref.manipulate_sample(x0, "deterministic", real_sigmoid_mean=real_mean)
+        sig, _ = mlp.score(x)
+        rej.sampling(x, sig, shift_percent=100.0)
+        mh.sampling(x, sig)
+        e.record()
+        e.synchronize()
+        if it >= 2:
+            best = min(best, s.elapsed_time(e) * 1e-3)
+    out = {"value": n / best, "unit": "refined points/s", "ms_per_pass": best * 1e3,
+           "workload": "2-D MLP D (2-64x5-1), N=%d, ladam K=%d, then DRS(p=100) and MH(T=20)" % (n, steps_k),
+           "mflop_per_point": 3.35}
+    if cpu:
+        from oracle import nets as onets
+        from oracle import sampling_np as snp
+        torch.set_num_threads(host_threads())
+        x0h = x0.cpu().numpy()
+        t0 = time.perf_counter()
+        o = snp.refine_2d(x0h, lambda x: onets.mlp2d_sigmoid_saliency(x, ws), np.float32(real_mean), steps_k, 0.1, "ladam")
+        sg, _ = onets.mlp2d_sigmoid_saliency(o["optimal_batch"], ws)
+        snp.drs_accept(sg, rng.rand(n), 0.0, shift_percent=100.0)
+        snp.mh_chain(sg, rng.rand(n), np.float32(real_mean), 1, 20, 0)
+        t = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / t, "unit": "refined points/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "same N, one pass (reference refiner_cpu algorithm, torch-CPU MLP)"}
+    return out
+
+
 def run_ours(args, wl):
     import numpy as np
     import torch
@@ -455,7 +506,8 @@ def run_ours(args, wl):
             # secondary workload named by north_star (DCGAN-64 CelebA shape, refine at layer 1, K=50, batch 1024):
             # same code path, reported beside the headline so both ends of the size range are on record
             try:
-                line["also"] = {"dcgan64_l1": measure_extra(torch, "dcgan64_l1", dev, args.math)}
+                line["also"] = {"dcgan64_l1": measure_extra(torch, "dcgan64_l1", dev, args.math),
+                                "synthetic2d": measure_2d(torch, dev, cpu=not args.no_cpu_baseline)}
             except RuntimeError as exc:        # e.g. out of memory on a shared box: never lose the headline line
                 line["also"] = {"dcgan64_l1": {"error": str(exc)[:200]}}
         if roof:
