@@ -373,7 +373,7 @@ def run_ours(args, wl):
     refiner.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     mh = IndependenceSampler(T=20, rng="philox", seed=2019)          # nsgan/GAN.py:169
     mh.set_score_curr(np.float32(0.5))
-    lo, hi = rank * batch, (rank + 1) * batch
+    bounds = [(r * batch, (r + 1) * batch) for r in range(world)]      # contiguous row block per rank
     h0_host = torch.from_numpy(S.proposal_features(arch, batch, seed=1000 + rank)).pin_memory()
     h0_dev = h0_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -385,7 +385,7 @@ def run_ours(args, wl):
         sig = D.gather_scores(sig_local) if world > 1 else sig_local
         emit = mh.select(sig)
         if world > 1:
-            acc = D.gather_accepted(x, emit.long(), lo, hi)
+            acc = D.gather_accepted(x, emit.long(), bounds)
         else:
             acc = mh.gather(x)                                   # cgs_gather_rows on the emitted source rows
         return x, acc, sig_local

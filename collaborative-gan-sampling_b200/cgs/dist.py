@@ -57,22 +57,25 @@ def owned_slice(src_global, lo, hi):
     return start, stop
 
 
-def gather_accepted(local_rows, src_global, lo, hi, group=None):
+def gather_accepted(local_rows, src_global, bounds, group=None):
     """All-gather(v) of the accepted rows in global order.
 
-    ``local_rows`` [n_local, ...] are this rank's samples (global rows lo..hi); ``src_global`` is the ascending
-    list of accepted / emitted GLOBAL row ids (identical on every rank).  Returns [len(src_global), ...].
+    ``local_rows`` [n_local, ...] are this rank's samples; ``bounds[r] = (lo, hi)`` are the global row blocks of every
+    rank (``shard_bounds``); ``src_global`` is the ascending list of accepted / emitted GLOBAL row ids, identical on
+    every rank because every rank evaluated the same global chain.  Ownership is a pure function of that list, so
+    all counts are known everywhere without a collective; one padded all_gather moves the rows.
+    Returns [len(src_global), ...] on every rank.
     """
     rank, ws = world()
+    lo, hi = bounds[rank]
     start, stop = owned_slice(src_global, lo, hi)
     mine = local_rows[(src_global[start:stop] - lo).long()] if stop > start else local_rows[:0]
     if ws == 1:
         return mine
     counts = []
-    for r in range(ws):
-        # ownership is a pure function of the global list, so every rank knows every count without a collective
-        rlo, rhi = _bounds_cache(src_global, r, ws, lo, hi, rank)
-        counts.append(rhi - rlo)
+    for rlo, rhi in bounds:
+        a, b = owned_slice(src_global, rlo, rhi)
+        counts.append(b - a)
     m = max(counts) if counts else 0
     if m == 0:
         return local_rows[:0]
@@ -81,27 +84,6 @@ def gather_accepted(local_rows, src_global, lo, hi, group=None):
     bufs = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)])
-
-
-_SHARDS = {}
-
-
-def set_shard_table(bounds):
-    """bounds[r] = (lo, hi) for every rank; needed when shards are ragged."""
-    _SHARDS["bounds"] = list(bounds)
-
-
-def _bounds_cache(src_global, r, ws, lo, hi, rank):
-    table = _SHARDS.get("bounds")
-    if table is None or len(table) != ws:
-        if r == rank:
-            rlo, rhi = lo, hi
-        else:
-            size = hi - lo                      # equal shards
-            rlo, rhi = r * size, (r + 1) * size
-    else:
-        rlo, rhi = table[r]
-    return owned_slice(src_global, rlo, rhi)
 
 
 def reduce_stats(n_accepted, score_sum, score_max, group=None):

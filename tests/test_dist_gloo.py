@@ -24,12 +24,8 @@ def _worker(rank, world, port, n_global, ragged, ret):
     scores = rng.beta(2, 5, size=n_global).astype(np.float32)
     rows = rng.randn(n_global, 3).astype(np.float32)
     u = rng.rand(n_global)
-    if ragged:
-        bounds = [D.shard_bounds(n_global, r, world) for r in range(world)]
-        D.set_shard_table(bounds)
-    else:
-        bounds = [(r * (n_global // world), (r + 1) * (n_global // world)) for r in range(world)]
-        D.set_shard_table(bounds)
+    bounds = [D.shard_bounds(n_global, r, world) for r in range(world)]
+    assert ragged == (len({hi - lo for lo, hi in bounds}) > 1)
     lo, hi = bounds[rank]
     local_scores = torch.from_numpy(scores[lo:hi])
     local_rows = torch.from_numpy(rows[lo:hi])
@@ -37,7 +33,7 @@ def _worker(rank, world, port, n_global, ragged, ret):
     assert torch.equal(g, torch.from_numpy(scores))
     # every rank runs the global chain redundantly on identical inputs -> identical emitted rows
     emit, _, _, _ = snp.mh_chain(g.numpy().reshape(-1, 1), u, np.float32(0.4), 1, 3, 0)
-    acc = D.gather_accepted(local_rows, torch.from_numpy(emit), lo, hi)
+    acc = D.gather_accepted(local_rows, torch.from_numpy(emit), bounds)
     assert torch.equal(acc, torch.from_numpy(rows[emit]))
     n, ssum, smax = D.reduce_stats(hi - lo, float(local_scores.double().sum()), float(local_scores.max()))
     assert n == n_global and abs(ssum - float(scores.astype(np.float64).sum())) < 1e-9 and smax == float(scores.max())
