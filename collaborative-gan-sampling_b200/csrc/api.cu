@@ -2,6 +2,7 @@
 #include "common.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace cgs {
 
@@ -13,6 +14,18 @@ char* error_buffer() {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
+
+static std::atomic<int> g_debug{-1};
+int debug_flags() {
+  int v = g_debug.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("CGS_DEBUG");
+    v = e ? atoi(e) : 0;
+    g_debug.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+void set_debug_flags(int v) { g_debug.store(v < 0 ? 0 : v, std::memory_order_relaxed); }
 
 int require_sm100() {
   static thread_local int cached_dev = -1;
@@ -41,4 +54,13 @@ namespace cgs { int debug_trace_read(unsigned long long* out, int cap); }
 // Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when CGS_DEBUG has bit 256 set.
 extern "C" __attribute__((visibility("default"))) int cgs_debug_trace(unsigned long long* out_host, int capacity) {
   return cgs::debug_trace_read(out_host, capacity);
+}
+
+namespace cgs { void set_debug_flags(int v); }
+// Developer aid: replace the CGS_DEBUG knobs at run time (bit 4096 = image-edge passes on the general tcgen05
+// lowerings, used by the parity tests to keep both implementations covered).  Returns the previous value.
+extern "C" __attribute__((visibility("default"))) int cgs_debug_set_flags(int flags) {
+  const int old = cgs::debug_flags();
+  cgs::set_debug_flags(flags);
+  return old;
 }

@@ -27,6 +27,9 @@ inline int check_launch(const char* what) {
 // The product never runs on anything but sm_100: refuse loudly instead of falling back.
 int require_sm100();
 
+// Developer knobs: env CGS_DEBUG at first use, overridable with cgs_debug_set_flags (api.cu).
+int debug_flags();
+
 // Process-wide count of kernels launched by the library (cgs_launch_count).
 void count_launch(int n = 1);
 

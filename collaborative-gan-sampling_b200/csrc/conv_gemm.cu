@@ -22,13 +22,13 @@
 namespace cgs {
 
 // ---- optional event trace of CTA 0 (CGS_DEBUG bit 256): (role, event, index, clock) records for pipeline analysis
-__device__ unsigned long long g_trace[16384];
+__device__ unsigned long long g_trace[32768];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ void trace(const ConvGemmParams& p, int role, int ev, unsigned idx) {
   // fixed slot per (role, event, index): a plain store, no atomics, so the traced thread is barely perturbed
   if ((p.debug & 256) && blockIdx.x == 0 && idx < 1024) {
     const unsigned slot = ((unsigned)(role * 4 + ev) << 10) + idx;
-    g_trace[slot & 16383] = ((unsigned long long)role << 60) | ((unsigned long long)ev << 56) |
+    g_trace[slot & 32767] = ((unsigned long long)role << 60) | ((unsigned long long)ev << 56) |
                             ((unsigned long long)(idx & 0xffffff) << 32) | (unsigned long long)(unsigned)clock64();
   }
 }
@@ -60,7 +60,12 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = KB * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // accumulator ring in TMEM: 4 buffers up to BN = 128 (512 columns), 2 for BN = 256
+  static constexpr int NACC = (BN >= 256) ? 2 : 4;
+  static constexpr int TMEM_COLS = NACC * BN;
+  // up to BN = 128 each epilogue warp group owns whole tiles (three tile epilogues in flight per CTA, the per-tile
+  // set-up paid by 4 warps instead of 12); at BN = 256 the groups split the 16 chunks of one tile
+  static constexpr bool SPLIT_TILES = (BN <= 128);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -79,8 +84,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
-  uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + C::NACC;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * C::NACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,9 +97,10 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       mbar_init(&full_bar[s], p.a_tma ? 2 : kProdWarps * 32 + 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < C::NACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], p.a_tma ? kMaxEpiWarps : kEpiWarps);  // one arrive per epilogue warp
+      // one arrive per epilogue warp that reads the buffer: the 4 warps of one group, or all groups at BN = 256
+      mbar_init(&tmem_empty_bar[a], (p.a_tma && !C::SPLIT_TILES) ? kMaxEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -205,9 +211,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const uint32_t smem_b_u32 = smem_u32(smem_b);
     uint32_t it_global = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ci = tile / tiles_per_class;
+      const int ci = fast_div(tile, p.fd_tiles_per_class);
       const int rem = tile - ci * tiles_per_class;
-      const int n_tile = rem % p.n_tiles;
+      const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
       const int katom0 = p.cls[ci].k0 / BK;
       const int nkb = p.cls[ci].nkb;
       for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
@@ -233,13 +239,14 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
       uint32_t it_global = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ci = tile / tiles_per_class;
+        const int ci = fast_div(tile, p.fd_tiles_per_class);
         const int rem = tile - ci * tiles_per_class;
-        const int m_tile = rem / p.n_tiles;
+        const int m_tile = fast_div(rem, p.fd_n_tiles);
         const GemmClass& gc = p.cls[ci];
         const int nkb = gc.nkb;
-        const int b0 = (m_tile / p.hy_tiles) * p.BB;
-        const int y_tile = (m_tile % p.hy_tiles) * p.BH * p.S;
+        const int mb = fast_div(m_tile, p.fd_hy_tiles);
+        const int b0 = mb * p.BB;
+        const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
         int t = 0, cb = 0;
         for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
           const int s = it_global % C::STAGES;
@@ -283,10 +290,10 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     uint32_t it_global = 0;
     uint32_t tile_count = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
-      const int ci = tile / tiles_per_class;
+      const int ci = fast_div(tile, p.fd_tiles_per_class);
       const int nkb = p.cls[ci].nkb;
-      const uint32_t acc = tile_count & 1;
-      const uint32_t acc_ph = (tile_count >> 1) & 1;
+      const uint32_t acc = tile_count % C::NACC;
+      const uint32_t acc_ph = (tile_count / C::NACC) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -322,49 +329,64 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    // warps 0-3 always; in TMA mode the 8 idle producer warps join.  A warp may only touch the TMEM lane quarter
-    // (warp % 4), so the warps of one quarter split the accumulator columns in 16-column chunks.
+    // warps 0-3 always; in TMA mode the 8 idle producer warps join as two more groups.  A warp may only touch the
+    // TMEM lane quarter (warp % 4).  Up to BN = 128 a group owns whole tiles (tile_count % groups), so three tile
+    // epilogues overlap and a tile's set-up is paid by 4 warps; at BN = 256 the groups split one tile's chunks.
     constexpr int Q = EPI_CH / 4;                  // float4 per staged row
     constexpr int ROWS_PER_PASS = 32 / Q;          // rows covered by one warp-wide 16-byte access
     constexpr int PASSES = 32 / ROWS_PER_PASS;
+    constexpr int NCH = BN / EPI_CH;
+    constexpr int MAXOWN = NCH >= 2 ? 2 : 1;       // chunks pulled out of TMEM per batch (2 x 16 registers)
     const int quarter = warp & 3;
     const int group = warp >> 2;                   // 0..2
     const int ngroups = p.a_tma ? kMaxEpiWarps / 4 : 1;
+    const int tile_groups = C::SPLIT_TILES ? ngroups : 1;    // groups that take separate tiles
+    const int chunk_groups = C::SPLIT_TILES ? 1 : ngroups;   // groups that share the chunks of one tile
+    const int chunk_first = C::SPLIT_TILES ? 0 : group;
     float* stage = smem_epi + warp * 32 * EPI_PITCH;
     const int c4 = lane % Q;
     const int rsub = lane / Q;
-    uint32_t tile_count = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
-      const int ci = tile / tiles_per_class;
-      const int rem = tile - ci * tiles_per_class;
-      const int m_tile = rem / p.n_tiles;
-      const int n_tile = rem - m_tile * p.n_tiles;
-      const GemmClass& gc = p.cls[ci];
-      const uint32_t acc = tile_count & 1;
-      const uint32_t acc_ph = (tile_count >> 1) & 1;
-      int row_off = -1;                            // element offset of this lane's row in out / aux / mom
-      {
-        const int r = quarter * 32 + lane;
-        const int bb = r / rows_per_img_tile;
-        const int q = r - bb * rows_per_img_tile;
-        const int hh = q / p.MW;
-        const int i = q - hh * p.MW;
-        const int b = (m_tile / p.hy_tiles) * p.BB + bb;
-        const int j = (m_tile % p.hy_tiles) * p.BH + hh;
-        if (r < p.rows_valid && b < p.B && j < p.MH)
-          row_off = ((b * p.OH + j * p.os + gc.oy0) * p.OW + (i * p.os + gc.ox0)) * p.ON;
-      }
-      int ro[PASSES];                              // row offsets of the rows this lane stores
+    // tile-invariant part of the row -> output offset map of the PASSES rows this lane stores
+    // (a tile spans either several whole images, BB > 1, or part of one image, BB == 1: one bound test per row)
+    const bool multi_img = p.BB > 1;
+    const int lim = multi_img ? p.B : p.MH;
+    int l_off[PASSES], l_pos[PASSES];
 #pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) ro[ps] = __shfl_sync(0xffffffffu, row_off, ps * ROWS_PER_PASS + rsub);
-      constexpr int NCH = BN / EPI_CH;
-      // chunks pulled out of TMEM per batch (2 x 16 registers); narrow tiles finish in a single batch
-      constexpr int MAXOWN = ((NCH + 2) / 3) < 2 ? ((NCH + 2) / 3) : 2;
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = quarter * 32 + ps * ROWS_PER_PASS + rsub;
+      const int bb = r / rows_per_img_tile;
+      const int q = r - bb * rows_per_img_tile;
+      const int hh = q / p.MW;
+      const int i = q - hh * p.MW;
+      l_off[ps] = ((bb * p.OH + hh * p.os) * p.OW + i * p.os) * p.ON;
+      l_pos[ps] = r < p.rows_valid ? (multi_img ? bb : hh) : (1 << 28);   // padding rows never pass the bound test
+    }
+    for (uint32_t tile_count = C::SPLIT_TILES ? group : 0;; tile_count += tile_groups) {
+      const int tile = blockIdx.x + tile_count * gridDim.x;
+      if (tile >= total_tiles) break;
+      const int ci = fast_div(tile, p.fd_tiles_per_class);
+      const int rem = tile - ci * tiles_per_class;
+      const int m_tile = fast_div(rem, p.fd_n_tiles);
+      const int n_tile = rem - m_tile * p.n_tiles;
+      const int mb = fast_div(m_tile, p.fd_hy_tiles);
+      const int b0 = mb * p.BB;
+      const int j0 = (m_tile - mb * p.hy_tiles) * p.BH;
+      const uint32_t acc = tile_count % C::NACC;
+      const uint32_t acc_ph = (tile_count / C::NACC) & 1;
+      const int t_off = ((b0 * p.OH + j0 * p.os + p.cls[ci].oy0) * p.OW + p.cls[ci].ox0) * p.ON;
+      int ro[PASSES];                              // element offset of each stored row in out / aux / mom, -1 = none
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps)
+        ro[ps] = ((multi_img ? b0 : j0) + l_pos[ps] < lim) ? t_off + l_off[ps] : -1;
+      // chunks of this tile that hold valid output channels (ON is a multiple of 4; the tail of the last n tile and
+      // the zero columns of a narrow N are never read out of TMEM)
+      const int n0 = n_tile * BN;
+      const int nch = (p.ON - n0) >= BN ? NCH : (p.ON - n0 + EPI_CH - 1) / EPI_CH;
       // epilogue operands (bias / forward output / feature + momentum) of a chunk, fetched ahead of its use
       float4 x0[PASSES], x1[PASSES];
       auto prefetch = [&](int ch) {
-        const int n = n_tile * BN + ch * EPI_CH + c4 * 4;
-        if (ch >= NCH || n >= p.ON) return;
+        const int n = n0 + ch * EPI_CH + c4 * 4;
+        if (ch >= nch || n >= p.ON) return;
         if (p.epi == EPI_BWD) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
@@ -380,22 +402,23 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           x0[0] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      prefetch(group);                             // in flight while the main loop of this tile still runs
+      prefetch(chunk_first);                       // in flight while the main loop of this tile still runs
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       bool released = false;
 #pragma unroll 1
-      for (int ch0 = group; ch0 < NCH || !released; ch0 += ngroups * MAXOWN) {
-        // pull a batch of this warp's chunks out of TMEM at once, then give the accumulator back before touching
-        // global memory (the next-but-one tile's MMAs are waiting for it)
+      for (int ch0 = chunk_first; ch0 < nch || !released; ch0 += chunk_groups * MAXOWN) {
+        // pull a batch of this warp's chunks out of TMEM at once; after the last batch give the accumulator back
+        // before touching global memory
         uint32_t v[MAXOWN][EPI_CH];
 #pragma unroll
         for (int u = 0; u < MAXOWN; ++u)
-          if (ch0 + u * ngroups < NCH) tmem_ld_32x32b_x16(taddr + (ch0 + u * ngroups) * EPI_CH, v[u]);
+          if (ch0 + u * chunk_groups < nch) tmem_ld_32x32b_x16(taddr + (ch0 + u * chunk_groups) * EPI_CH, v[u]);
         tmem_ld_wait();
-        if (ch0 + ngroups * MAXOWN >= NCH) {
+        if (warp == 0 && lane == 0) trace(p, 4, 0, tile_count * 8 + ch0);
+        if (ch0 + chunk_groups * MAXOWN >= nch) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -404,10 +427,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         }
 #pragma unroll
         for (int u = 0; u < MAXOWN; ++u) {
-          const int ch = ch0 + u * ngroups;
-          if (ch >= NCH) break;
-          const int nbase = n_tile * BN + ch * EPI_CH;
-          if (nbase >= p.ON || (p.debug & 16)) continue;        // warp-uniform
+          const int ch = ch0 + u * chunk_groups;
+          if (ch >= nch) break;
+          if (p.debug & 16) continue;                          // warp-uniform
           // lane = row: stage 32 rows x 16 columns, then re-read with lane = (row group, 16-byte column)
 #pragma unroll
           for (int q4 = 0; q4 < Q; ++q4)
@@ -415,7 +437,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
                 make_float4(__uint_as_float(v[u][4 * q4]), __uint_as_float(v[u][4 * q4 + 1]),
                             __uint_as_float(v[u][4 * q4 + 2]), __uint_as_float(v[u][4 * q4 + 3]));
           __syncwarp();
-          const int n = nbase + c4 * 4;
+          const int n = n0 + ch * EPI_CH + c4 * 4;
           const bool n_ok = n < p.ON;                // ON is a multiple of 4
           float4 a[PASSES];
 #pragma unroll
@@ -425,11 +447,14 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
             if (ro[ps] >= 0 && n_ok) o[ps] = epilogue4(p, ro[ps] + n, a[ps], p.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
-          if (!(p.debug & 2048)) prefetch(ch + ngroups);   // operands of the next chunk: overlap with these stores
+          if (warp == 0 && lane == 0) trace(p, 4, 1, tile_count * 8 + ch);
+          if (!(p.debug & 2048)) prefetch(ch + chunk_groups);   // operands of the next chunk: overlap with these stores
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
             if (ro[ps] >= 0 && n_ok && !(p.debug & 1024)) *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o[ps];
+          if (warp == 0 && lane == 0) trace(p, 4, 2, tile_count * 8 + ch);
           __syncwarp();
+          if (warp == 0 && lane == 0) trace(p, 4, 3, tile_count * 8 + ch);
         }
       }
       if (warp == 0 && lane == 0) trace(p, 3, 2, tile_count);
@@ -566,11 +591,7 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("CGS_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.debug = dbg;
-  }
+  p.debug = debug_flags();
   p.n_tiles = (p.N + BN - 1) / BN;
   // tile geometry: BB images x BH rows x MW columns (<= 128 rows) per row tile
   const int per_img = p.MH * p.MW;
@@ -629,7 +650,12 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.nclasses;
+  const long long total_ll = (long long)p.m_tiles * p.n_tiles * p.nclasses;
+  if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
+  const int total = (int)total_ll;
+  p.fd_tiles_per_class = fast_div_magic((unsigned)(p.m_tiles * p.n_tiles));
+  p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
+  p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
   const int grid = total < num_sms ? total : num_sms;
   conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap, tmap_a); count_launch();
   cudaError_t e = cudaGetLastError();
@@ -659,9 +685,9 @@ int validate(const ConvGemmParams& p, int w_cols) {
 
 int debug_trace_read(unsigned long long* out, int cap) {
   cudaDeviceSynchronize();
-  const int n = cap < 16384 ? cap : 16384;
+  const int n = cap < 32768 ? cap : 32768;
   cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long));
-  static unsigned long long zeros[16384];
+  static unsigned long long zeros[32768];
   cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
   return n;
 }

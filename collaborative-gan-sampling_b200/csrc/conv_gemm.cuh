@@ -67,6 +67,8 @@ struct ConvGemmParams {
   int act_tanh;       // act == tanh (slow path)
   int round_out;      // round results to TF32 (RN) because the next consumer is a kind::tf32 MMA
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
+  // exact division of the persistent tile index by multiply-shift (filled by the launcher; see fast_div)
+  unsigned long long fd_tiles_per_class, fd_n_tiles, fd_hy_tiles;
   GemmClass cls[kMaxClasses];
 };
 
@@ -86,6 +88,13 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
     case ACT_TANH: return 1.f - y * y;
     default: return 1.f;
   }
+}
+
+// n / d by multiply-high with magic = ceil(2^64 / d) (0 encodes d == 1): with magic * d = 2^64 + e, 0 <= e < d, the
+// excess n * e / (d * 2^64) stays below 1 / d for every 32-bit n, so the floor is exact
+inline unsigned long long fast_div_magic(unsigned d) { return d <= 1 ? 0ull : (~0ull) / d + 1ull; }
+__device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
+  return magic ? (int)__umul64hi((unsigned long long)(unsigned)n, magic) : n;
 }
 
 __device__ __forceinline__ float tf32_rn(float x) {

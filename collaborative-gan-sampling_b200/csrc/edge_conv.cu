@@ -1,0 +1,437 @@
+// Image-edge passes (see edge_conv.cuh): fused im2col / col2im + mma.sync TF32 + epilogue streaming kernels.
+//
+// Reference semantics: nsgan/ops.py:41 (conv2d, k x k, stride 2, SAME), nsgan/ops.py:55 (deconv2d) and their
+// tf.gradients data-gradients (sampling/collaborator.py:31); epilogues as in conv_gemm.cuh.
+#include "edge_conv.cuh"
+
+#include <cstdint>
+
+#include "common.h"
+#include "conv_gemm.cuh"
+
+namespace cgs {
+
+namespace {
+
+// D(16x8, fp32) += A(16x8, tf32, row) * B(8x8, tf32, col); g = lane / 4, t = lane % 4:
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Scalar twin of epilogue4 (conv_gemm.cuh): same formulas, same separately rounded policy arithmetic.
+__device__ __forceinline__ float epilogue1(const EdgeEpi& e, float a, float x0, float x1, float* m_out) {
+  float o = a;
+  if (e.epi == EPI_FWD) {
+    const float v = a + x0;
+    o = e.act_tanh ? tanhf(v) : fmaxf(v, v * e.slope);
+  } else if (e.epi == EPI_BWD) {
+    o = e.act_tanh ? a * (1.f - x0 * x0) : a * (x0 > 0.f ? 1.f : e.slope);
+  } else if (e.epi == EPI_UPDATE) {
+    float m = __fmul_rn(e.rate, a);                                   // sampling/policy.py:27-37
+    if (!e.sgd) {
+      if (!e.first) m = __fadd_rn(__fmul_rn(e.alpha, x1), m);
+      *m_out = m;
+    }
+    o = __fsub_rn(x0, m);
+    if (e.clip) o = fminf(fmaxf(o, e.vmin), e.vmax);                  // collaborator.py:69-70
+    return o;
+  }
+  return e.round_out ? tf32_rn(o) : o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge_wide: M = B*OH*OW output pixels, N = 64, K = k*k*cimg gathered from the pitched image through L1.
+// CTA = 4 warps, each 32 pixels x 64 channels per tile (2 x 8 mma tiles per k-step); weights live in shared
+// memory in fragment order, so a B fragment is one conflict-free LDS.64.
+// ---------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 128;
+constexpr int EW_NT = 8;            // N = 64
+constexpr int EW_KMAX = 104;        // k <= 5, cimg <= 4
+
+// Epilogue modes compiled into the kernel (the per-element code must stay a handful of instructions: it runs 64
+// times per thread and tile): slope-type forward / derivative, the policy step, and a generic fallback (tanh, raw).
+enum : int { EM_FWD_SLOPE = 0, EM_BWD_SLOPE = 1, EM_UPDATE = 2, EM_GENERIC = 3 };
+
+template <int MODE, bool ROUND>
+__device__ __forceinline__ float epi_fast(const EdgeEpi& e, float a, float x0, float x1, float* m_out) {
+  float o;
+  if (MODE == EM_FWD_SLOPE) {
+    const float v = a + x0;
+    o = fmaxf(v, v * e.slope);
+  } else if (MODE == EM_BWD_SLOPE) {
+    o = a * (x0 > 0.f ? 1.f : e.slope);
+  } else {
+    return epilogue1(e, a, x0, x1, m_out);
+  }
+  return ROUND ? tf32_rn(o) : o;
+}
+
+template <int MODE, bool ROUND>
+__global__ void __launch_bounds__(EW_THREADS) edge_wide_kernel(const EdgeWideParams p, int ksteps, int ntiles,
+                                                               unsigned long long fd_img, unsigned long long fd_ow) {
+  extern __shared__ float2 ew_bfrag[];   // [ksteps][8][32]
+  __shared__ int koff_s[EW_KMAX];
+  __shared__ int kdy_s[EW_KMAX];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int kreal = p.k * p.k * p.cimg;
+  for (int kk = tid; kk < ksteps * 8; kk += EW_THREADS) {
+    int off = 0, dy = 1 << 20;                 // padding k entries never pass the row test
+    if (kk < kreal) {
+      const int tap = kk / p.cimg, c = kk - tap * p.cimg;
+      const int ky = tap / p.k, kx = tap - ky * p.k;
+      off = ((ky - p.pad_y) * p.pitch + (kx - p.pad_x + p.xoff)) * 4 + c;
+      dy = ky - p.pad_y;
+    }
+    koff_s[kk] = off;
+    kdy_s[kk] = dy;
+  }
+  for (int idx = tid; idx < ksteps * EW_NT * 32; idx += EW_THREADS) {
+    const int l = idx & 31, nt = (idx >> 5) % EW_NT, ks = idx / (EW_NT * 32);
+    const int n = nt * 8 + (l >> 2);
+    float b[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = ks * 8 + (l & 3) + 4 * h;
+      b[h] = 0.f;
+      if (kk < kreal && n < p.N) {
+        const int tap = kk / p.cimg, c = kk - tap * p.cimg;
+        const int ky = tap / p.k, kx = tap - ky * p.k;
+        b[h] = __ldg(p.w + (size_t)n * (p.k * 32) + ky * 32 + kx * 4 + c);
+      }
+    }
+    ew_bfrag[idx] = make_float2(b[0], b[1]);
+  }
+  float2 bias2[EW_NT];
+#pragma unroll
+  for (int nt = 0; nt < EW_NT; ++nt)
+    bias2[nt] = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float2*>(p.e.bias + nt * 8 + 2 * t))
+                                                 : make_float2(0.f, 0.f);
+  __syncthreads();
+
+  const int per_img = p.OH * p.OW;
+  const int M = (int)p.M;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // the four pixels (rows of the two m16 tiles) this thread gathers for and stores
+    int base[4], y0[4], mrow[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = tile * 128 + warp * 32 + (r >> 1) * 16 + (r & 1) * 8 + g;
+      mrow[r] = m;
+      if (m < M) {
+        const int b = fast_div(m, fd_img);
+        const int q = m - b * per_img;
+        const int oy = fast_div(q, fd_ow), ox = q - oy * p.OW;
+        base[r] = ((b * p.IH + 2 * oy) * p.pitch + 2 * ox) * 4;
+        y0[r] = 2 * oy;
+      } else {
+        base[r] = 0;
+        y0[r] = -(1 << 21);
+      }
+    }
+    float acc[2][EW_NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < EW_NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int o0 = koff_s[ks * 8 + t], d0 = kdy_s[ks * 8 + t];
+      const int o1 = koff_s[ks * 8 + t + 4], d1 = kdy_s[ks * 8 + t + 4];
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = mt * 2 + h;
+          const bool v0 = (unsigned)(y0[r] + d0) < (unsigned)p.IH;
+          const bool v1 = (unsigned)(y0[r] + d1) < (unsigned)p.IH;
+          a[mt][h] = v0 ? __float_as_uint(__ldg(p.in + base[r] + o0)) : 0u;
+          a[mt][2 + h] = v1 ? __float_as_uint(__ldg(p.in + base[r] + o1)) : 0u;
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < EW_NT; ++nt) {
+        const float2 b = ew_bfrag[(ks * EW_NT + nt) * 32 + lane];
+        mma_tf32(acc[0][nt], a[0][0], a[0][1], a[0][2], a[0][3], __float_as_uint(b.x), __float_as_uint(b.y));
+        mma_tf32(acc[1][nt], a[1][0], a[1][1], a[1][2], a[1][3], __float_as_uint(b.x), __float_as_uint(b.y));
+      }
+    }
+    // epilogue: thread owns columns nt*8 + 2t, +1 of its four rows; a quad writes one 32-byte sector
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (mrow[r] >= M) continue;
+      const int mt = r >> 1, h = r & 1;
+      float* orow = p.out + (size_t)mrow[r] * p.ON + 2 * t;
+      float2 x0[EW_NT], x1[EW_NT];
+      if (MODE == EM_FWD_SLOPE) {
+#pragma unroll
+        for (int nt = 0; nt < EW_NT; ++nt) x0[nt] = bias2[nt];
+      } else if (MODE == EM_BWD_SLOPE) {
+        const float* arow = p.e.aux + (size_t)mrow[r] * p.ON + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < EW_NT; ++nt) x0[nt] = __ldg(reinterpret_cast<const float2*>(arow + nt * 8));
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < EW_NT; ++nt) {
+          x0[nt] = bias2[nt];
+          x1[nt] = make_float2(0.f, 0.f);
+          if (p.e.epi == EPI_BWD) {
+            x0[nt] = __ldg(reinterpret_cast<const float2*>(p.e.aux + (size_t)mrow[r] * p.ON + 2 * t + nt * 8));
+          } else if (p.e.epi == EPI_UPDATE) {
+            x0[nt] = *reinterpret_cast<const float2*>(orow + nt * 8);
+            if (!p.e.sgd && !p.e.first)
+              x1[nt] = *reinterpret_cast<const float2*>(p.e.mom + (size_t)mrow[r] * p.ON + 2 * t + nt * 8);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < EW_NT; ++nt) {
+        float2 m2 = make_float2(0.f, 0.f), o;
+        o.x = epi_fast<MODE, ROUND>(p.e, acc[mt][nt][2 * h], x0[nt].x, x1[nt].x, &m2.x);
+        o.y = epi_fast<MODE, ROUND>(p.e, acc[mt][nt][2 * h + 1], x0[nt].y, x1[nt].y, &m2.y);
+        if (MODE >= EM_UPDATE && p.e.epi == EPI_UPDATE && !p.e.sgd)
+          *reinterpret_cast<float2*>(p.e.mom + (size_t)mrow[r] * p.ON + 2 * t + nt * 8) = m2;
+        *reinterpret_cast<float2*>(orow + nt * 8) = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge_narrow: per tile (image b, band of R input rows + halo) compute col[pixel][(ky,kx,c)] = in[pixel][:] . W with
+// mma.sync (A fragments straight from global memory as 16-byte loads, K permuted so that a float4 feeds two k-steps),
+// park col in shared memory, then every output pixel of the band sums its taps in a fixed order (ky, kx ascending)
+// and applies the epilogue.  K = 64.
+// ---------------------------------------------------------------------------------------------
+constexpr int EN_THREADS = 256;
+constexpr int EN_ROWS = 256;        // col rows (input pixels incl. halo) per tile
+constexpr int EN_KSTEPS = 8;        // K = 64
+
+template <int NT, int CI>
+__global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarrowParams p, int ntiles) {
+  constexpr int CP = NT * 8 + 4;    // col row pitch (floats)
+  extern __shared__ float2 en_smem[];
+  float2* bfrag = en_smem;                                              // [8][NT][32]
+  float* col_s = reinterpret_cast<float*>(en_smem + EN_KSTEPS * NT * 32);   // [EN_ROWS][CP]
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nreal = p.k * p.k * CI;
+  for (int idx = tid; idx < EN_KSTEPS * NT * 32; idx += EN_THREADS) {
+    const int l = idx & 31, nt = (idx >> 5) % NT, ks = idx / (NT * 32);
+    const int n = nt * 8 + (l >> 2);
+    // logical k slots (t, t+4) of k-step ks are input channels 16*(ks/2) + 4t + 2*(ks%2) + {0, 1}
+    const int ch = 16 * (ks >> 1) + 4 * (l & 3) + 2 * (ks & 1);
+    float2 b = make_float2(0.f, 0.f);
+    if (n < nreal) {
+      const int tap = n / CI, c = n - tap * CI;
+      b = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)(tap * 4 + c) * p.K + ch));
+    }
+    bfrag[idx] = b;
+  }
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / p.bands;
+    const int r0 = (tile - b * p.bands) * p.R;
+    const int iy_lo = max(0, r0 - p.halo_lo);
+    const int iy_hi = min(p.IH, r0 + p.R + p.halo_hi);
+    const int mt_rows = (iy_hi - iy_lo) * p.IW;
+    const float* src = p.in + ((size_t)b * p.IH + iy_lo) * p.IW * p.K;
+    const int nmt = (mt_rows + 15) >> 4;
+    for (int mt = warp; mt < nmt; mt += EN_THREADS / 32) {
+      const int ra = mt * 16 + g, rb = ra + 8;
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        va[j] = ra < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)ra * p.K + 16 * j + 4 * t))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[j] = rb < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)rb * p.K + 16 * j + 4 * t))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float2 be = bfrag[((2 * j) * NT + nt) * 32 + lane];
+          mma_tf32(acc[nt], __float_as_uint(va[j].x), __float_as_uint(vb[j].x), __float_as_uint(va[j].y),
+                   __float_as_uint(vb[j].y), __float_as_uint(be.x), __float_as_uint(be.y));
+          const float2 bo = bfrag[((2 * j + 1) * NT + nt) * 32 + lane];
+          mma_tf32(acc[nt], __float_as_uint(va[j].z), __float_as_uint(vb[j].z), __float_as_uint(va[j].w),
+                   __float_as_uint(vb[j].w), __float_as_uint(bo.x), __float_as_uint(bo.y));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        *reinterpret_cast<float2*>(col_s + ra * CP + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(col_s + rb * CP + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+      }
+    }
+    __syncthreads();
+    // col2im + epilogue over the band's output rows (margins of the pitched layout are written as zeros): one warp
+    // per output row, so the ky taps are warp-uniform; only taps of the right parity are visited
+    const int y_lo = 2 * r0;
+    const int y_hi = min(p.OH, 2 * (r0 + p.R));
+    const int rows_in = iy_hi - iy_lo;
+    const float4 bias4 = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float4*>(p.e.bias))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = y_lo + warp; y < y_hi; y += EN_THREADS / 32) {
+      const int ky0 = (y + p.pad_y) & 1;
+      float* orow = p.out + ((size_t)b * p.OH + y) * p.out_pitch * 4;
+      for (int xc = lane; xc < p.out_pitch; xc += 32) {
+        const int x = xc - p.out_xoff;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (x >= 0 && x < p.OW) {
+          float a[CI];
+#pragma unroll
+          for (int c = 0; c < CI; ++c) a[c] = 0.f;
+          const int kx0 = (x + p.pad_x) & 1;
+          for (int ky = ky0; ky < p.k; ky += 2) {
+            const int lr = ((y + p.pad_y - ky) >> 1) - iy_lo;      // negative (above the image / tile) -> skipped
+            if ((unsigned)lr >= (unsigned)rows_in) continue;
+            for (int kx = kx0; kx < p.k; kx += 2) {
+              const int ix = (x + p.pad_x - kx) >> 1;
+              if ((unsigned)ix >= (unsigned)p.IW) continue;
+              const float* cp = col_s + (lr * p.IW + ix) * CP + (ky * p.k + kx) * CI;
+#pragma unroll
+              for (int c = 0; c < CI; ++c) a[c] += cp[c];
+            }
+          }
+          float4 x0 = bias4;
+          if (p.e.epi == EPI_BWD) x0 = __ldg(reinterpret_cast<const float4*>(p.e.aux + ((size_t)b * p.OH + y) * p.out_pitch * 4 + xc * 4));
+          const float xs[3] = {x0.x, x0.y, x0.z};
+          float unused;
+#pragma unroll
+          for (int c = 0; c < CI; ++c) o[c] = epilogue1(p.e, a[c], xs[c], 0.f, &unused);
+        }
+        *reinterpret_cast<float4*>(orow + xc * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int NT, int CI>
+int launch_narrow_nt(const EdgeNarrowParams& p, cudaStream_t st) {
+  constexpr int CP = NT * 8 + 4;
+  constexpr size_t smem = (size_t)EN_KSTEPS * NT * 32 * sizeof(float2) + (size_t)EN_ROWS * CP * sizeof(float);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(edge_narrow_kernel<NT, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_narrow): %s", cudaGetErrorString(e));
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, edge_narrow_kernel<NT, CI>, EN_THREADS, smem);
+    if (e != cudaSuccess || n < 1) return set_error(CGS_ERR_CUDA, "edge_narrow occupancy query failed");
+    ctas_per_sm = n;
+  }
+  const long long tiles = (long long)p.B * p.bands;
+  if (tiles >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large; split the batch");
+  long long grid = (long long)num_sms() * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  edge_narrow_kernel<NT, CI><<<(int)grid, EN_THREADS, smem, st>>>(p, (int)tiles);
+  count_launch();
+  return check_launch("edge_narrow_kernel");
+}
+
+}  // namespace
+
+bool edge_wide_supported(int N, int k, int cimg) {
+  return N == 64 && k >= 1 && k <= 5 && cimg >= 1 && cimg <= 4;
+}
+
+bool edge_narrow_supported(int K, int k, int cimg, int IW) {
+  return K == 64 && (k == 4 || k == 5) && (cimg == 1 || cimg == 3) && IW <= EN_ROWS / 4;
+}
+
+template <int MODE, bool ROUND>
+int launch_wide_mode(const EdgeWideParams& p, int ksteps, int tiles, cudaStream_t st) {
+  const size_t smem = (size_t)ksteps * EW_NT * 32 * sizeof(float2);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, edge_wide_kernel<MODE, ROUND>, EW_THREADS,
+                                                                  (size_t)13 * EW_NT * 32 * sizeof(float2));
+    if (e != cudaSuccess || n < 1) return set_error(CGS_ERR_CUDA, "edge_wide occupancy query failed");
+    ctas_per_sm = n;
+  }
+  int grid = num_sms() * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  edge_wide_kernel<MODE, ROUND><<<grid, EW_THREADS, smem, st>>>(p, ksteps, tiles, fast_div_magic((unsigned)(p.OH * p.OW)),
+                                                                  fast_div_magic((unsigned)p.OW));
+  count_launch();
+  return check_launch("edge_wide_kernel");
+}
+
+int launch_edge_wide(const EdgeWideParams& p, cudaStream_t st) {
+  if (p.M <= 0) return CGS_OK;
+  const int ksteps = (p.k * p.k * p.cimg + 7) / 8;
+  if (p.M * p.ON >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit indexing; split the batch");
+  const int tiles = (int)((p.M + 127) / 128);
+  const bool rnd = p.e.round_out != 0;
+  if (p.e.epi == EPI_FWD && !p.e.act_tanh)
+    return rnd ? launch_wide_mode<EM_FWD_SLOPE, true>(p, ksteps, tiles, st) : launch_wide_mode<EM_FWD_SLOPE, false>(p, ksteps, tiles, st);
+  if (p.e.epi == EPI_BWD && !p.e.act_tanh)
+    return rnd ? launch_wide_mode<EM_BWD_SLOPE, true>(p, ksteps, tiles, st) : launch_wide_mode<EM_BWD_SLOPE, false>(p, ksteps, tiles, st);
+  if (p.e.epi == EPI_UPDATE) return launch_wide_mode<EM_UPDATE, false>(p, ksteps, tiles, st);
+  return launch_wide_mode<EM_GENERIC, false>(p, ksteps, tiles, st);
+}
+
+int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
+  if (p.B <= 0) return CGS_OK;
+  // rows of the input needed above / below a band of R input rows (its 2R output rows gather taps
+  // iy = (y + pad_y - ky) / 2): brute force over a sample band, the answer does not depend on R or r0
+  int lo = 0, hi = 0;
+  {
+    const int Rs = 8;
+    for (int y = 0; y < 2 * Rs; ++y)
+      for (int ky = 0; ky < p.k; ++ky) {
+        const int ty = y + p.pad_y - ky;
+        if (ty & 1) continue;
+        const int iy = ty >= 0 ? ty / 2 : -((-ty) / 2);
+        if (-iy > lo) lo = -iy;
+        if (iy - (Rs - 1) > hi) hi = iy - (Rs - 1);
+      }
+  }
+  p.halo_lo = lo;
+  p.halo_hi = hi;
+  const int rows_max = EN_ROWS / p.IW;
+  if (p.IH <= rows_max) {
+    p.R = p.IH;
+  } else {
+    p.R = rows_max - lo - hi;
+    if (p.R < 1) return set_error(CGS_ERR_UNSUPPORTED, "edge_narrow: image row too wide for the tile");
+  }
+  p.bands = (p.IH + p.R - 1) / p.R;
+  if (p.k == 4 && p.cimg == 1) return launch_narrow_nt<2, 1>(p, st);
+  if (p.k == 5 && p.cimg == 1) return launch_narrow_nt<4, 1>(p, st);
+  if (p.k == 4 && p.cimg == 3) return launch_narrow_nt<6, 3>(p, st);
+  if (p.k == 5 && p.cimg == 3) return launch_narrow_nt<10, 3>(p, st);
+  return set_error(CGS_ERR_UNSUPPORTED, "edge_narrow: unsupported k / channel combination");
+}
+
+}  // namespace cgs

@@ -2,6 +2,7 @@
 // BCE gradient + best-of-K select + image keep), and the K-step loop of sampling/collaborator.py:41-88.
 #include "common.h"
 #include "conv_gemm.cuh"
+#include "edge_conv.cuh"
 
 #include <cstring>
 
@@ -397,6 +398,28 @@ struct PassEpi {
   const ConvGemmParams* upd = nullptr;   // EPI_UPDATE fields
 };
 
+// Epilogue description of an image-edge kernel (edge_conv.cuh) from the pass epilogue.
+EdgeEpi make_edge_epi(const PassEpi& e, const float* bias) {
+  EdgeEpi x;
+  std::memset(&x, 0, sizeof(x));
+  x.epi = e.epi;
+  x.act_tanh = (e.act == ACT_TANH);
+  x.slope = e.act == ACT_RELU ? 0.f : (e.act == ACT_LRELU ? 0.2f : 1.f);
+  x.round_out = e.round_out;
+  x.bias = (e.epi == EPI_FWD) ? bias : nullptr;
+  x.aux = e.aux;
+  if (e.upd) {
+    x.epi = EPI_UPDATE;
+    x.mom = e.upd->mom; x.first = e.upd->first; x.sgd = e.upd->sgd; x.rate = e.upd->rate; x.alpha = e.upd->alpha;
+    x.clip = e.upd->clip; x.vmin = e.upd->vmin; x.vmax = e.upd->vmax;
+    x.round_out = 0;
+  }
+  return x;
+}
+
+// CGS_DEBUG bit 4096 (or cgs_debug_set_flags): keep the image-edge passes on the general tcgen05 lowerings
+bool edge_kernels_enabled() { return !(debug_flags() & 4096); }
+
 int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int math, cudaStream_t stream) {
   if (math == CGS_MATH_FP32_SIMT) return launch_conv_gemm_simt(p, w, rows, cols, stream);
   if (math == CGS_MATH_TF32_TENSOR) return launch_conv_gemm_tc(p, w, rows, cols, stream);
@@ -413,6 +436,29 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
   if (use_scatter(L, backward)) {
     if (!col) return set_error(CGS_ERR_WORKSPACE, "scatter pass needs a column workspace");
     if (rows != scatter_cols(L)) return set_error(CGS_ERR_INVALID, "weights of this pass must be in scatter layout (%d rows)", scatter_cols(L));
+    {
+      const LayerShape s = layer_shape(L);
+      const int kch = backward ? L.cout : L.cin, cimg = backward ? L.cin : L.cout;
+      const int iw = backward ? s.wout : L.win;
+      if (math == CGS_MATH_TF32_TENSOR && edge_kernels_enabled() && !e.upd && edge_narrow_supported(kch, L.k, cimg, iw) &&
+          cols == kch) {
+        EdgeNarrowParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.in = in; q.out = out; q.w = w;
+        q.B = (int)B; q.K = kch; q.k = L.k; q.cimg = cimg;
+        if (!backward) {
+          q.IH = L.hin; q.IW = L.win; q.OH = s.hout; q.OW = s.wout;
+          q.pad_y = same_pad_before(s.hout, L.k); q.pad_x = same_pad_before(s.wout, L.k);
+        } else {
+          q.IH = s.hout; q.IW = s.wout; q.OH = L.hin; q.OW = L.win;
+          q.pad_y = same_pad_before(L.hin, L.k); q.pad_x = same_pad_before(L.win, L.k);
+        }
+        q.out_pitch = dense_image ? q.OW : img_pitch(q.OW);
+        q.out_xoff = dense_image ? 0 : IMG_XOFF;
+        q.e = make_edge_epi(e, L.bias);
+        return launch_edge_narrow(q, st);
+      }
+    }
     ConvGemmParams p;
     if (int rc = make_scatter_gemm_params(L, backward, B, in, col, p)) return rc;
     if (int rc = launch_gemm(p, w, rows, cols, math, st)) return rc;
@@ -447,6 +493,18 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     if (rows != (backward ? L.cin : L.cout) || cols != window_kcols(L))
       return set_error(CGS_ERR_INVALID, "weights of this pass must be in window layout (%d columns)", window_kcols(L));
     if (int rc = make_window_params(L, backward, B, in, out, p)) return rc;
+    const int cimg = backward ? L.cout : L.cin;
+    if (math == CGS_MATH_TF32_TENSOR && edge_kernels_enabled() && edge_wide_supported(p.N, L.k, cimg) && p.ON == p.N) {
+      EdgeWideParams q;
+      std::memset(&q, 0, sizeof(q));
+      q.in = in; q.out = out; q.w = w;
+      q.IH = p.IH; q.pitch = p.in_pitch_px; q.xoff = IMG_XOFF; q.OH = p.OH; q.OW = p.OW; q.ON = p.ON; q.N = p.N;
+      q.k = L.k; q.cimg = cimg;
+      q.pad_y = same_pad_before(p.IH, L.k); q.pad_x = same_pad_before(p.IW, L.k);
+      q.M = (long long)B * p.OH * p.OW;
+      q.e = make_edge_epi(e, backward ? nullptr : L.bias);
+      return launch_edge_wide(q, st);
+    }
   } else if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) {
     return rc;
   }

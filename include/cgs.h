@@ -240,6 +240,10 @@ CGS_API int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, con
 
 /* Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when env CGS_DEBUG has bit 256 set. */
 CGS_API int cgs_debug_trace(unsigned long long* out_host, int capacity);
+/* Developer aid: replace the CGS_DEBUG knobs at run time; returns the previous value.  Bit 4096 routes the image-edge
+ * passes (first D conv / last G deconv and their data-gradients) through the general tcgen05 lowerings instead of
+ * the fused streaming kernels of csrc/edge_conv.cu. */
+CGS_API int cgs_debug_set_flags(int flags);
 
 #ifdef __cplusplus
 }

@@ -29,8 +29,22 @@ def pad_c(x, cs):
     return out
 
 
+@pytest.fixture
+def general_lowering(cgs_lib):
+    """Route the image-edge passes through the general tcgen05 lowerings (CGS_DEBUG bit 4096) for one test."""
+    old = cgs_lib.cgs_debug_set_flags(4096)
+    yield
+    cgs_lib.cgs_debug_set_flags(old)
+
+
+@pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("mnist", 67), ("dcgan64_l2", 2)])
+def test_edge_layers_general_lowering(cgs_lib, cuda_device, general_lowering, arch_name, B):
+    """The tcgen05 window / scatter lowerings stay covered although the fused edge kernels are the default."""
+    test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, "tf32")
+
+
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
-@pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("dcgan32_l1", 3), ("dcgan64_l2", 2)])
+@pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("mnist", 67), ("dcgan32_l1", 3), ("dcgan64_l2", 2), ("dcgan64_l2", 9)])
 def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
     from cgs import lib as L
     from cgs import nets as N

@@ -33,19 +33,27 @@ elif layer["type"] == "conv":
 else:
     xs = (B, layer["hin"], layer["win"], N.cstride(cin)); ys = (B, layer["hin"] * 2, layer["win"] * 2, N.cstride(cout))
 x = torch.randn(xs, device=dev); y = torch.empty(ys, device=dev); dy = torch.randn(ys, device=dev); dx = torch.empty(xs, device=dev)
-buf = np.zeros(16384, np.uint64)
+buf = np.zeros(32768, np.uint64)
 ws = torch.empty(int(lib.cgs_layer_workspace_bytes(C.byref(desc), B)), dtype=torch.uint8, device=dev)
 for rep in range(2):
     if a.bwd:
         L.check(lib.cgs_layer_backward(C.byref(desc), 0, B, L.ptr(dy), L.ptr(dx), L.ptr(x), 1, L.ptr(ws), ws.numel(), L.stream_ptr()))
     else:
         L.check(lib.cgs_layer_forward(C.byref(desc), 0, B, L.ptr(x), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
-    n = lib.cgs_debug_trace(buf.ctypes.data, 16384)
+    n = lib.cgs_debug_trace(buf.ctypes.data, 32768)
 ev = [(int(v >> 60), int((v >> 56) & 0xf), int((v >> 32) & 0xffffff), int(v & 0xffffffff)) for v in buf[:n].tolist() if v]
 t0 = min(e[3] for e in ev)
 names = {(0, 0): "P.wait_empty", (0, 1): "P.issued", (1, 0): "T.wait_empty", (2, 0): "M.wait_full", (2, 1): "M.commit",
-         (2, 2): "M.tmem_empty", (3, 0): "E.tmem_full", (3, 1): "E.released", (3, 2): "E.done"}
+         (2, 2): "M.tmem_empty", (3, 0): "E.tmem_full", (3, 1): "E.released", (3, 2): "E.done",
+         (4, 0): "C.ld_done", (4, 1): "C.math_done", (4, 2): "C.stored", (4, 3): "C.synced"}
 print("events", len(ev))
+chunk = {}
+for e in ev:
+    if e[0] == 4:
+        chunk.setdefault(e[2], {})[e[1]] = (e[3] - t0) & 0xffffffff
+print("per chunk (idx = tile_count*8 + chunk): ld_done math_done stored synced")
+for k in sorted(chunk)[:24]:
+    print("   %4d  %s" % (k, "  ".join("%7d" % chunk[k].get(i, -1) for i in range(4))))
 for key in sorted(names):
     rows = sorted([(e[2], (e[3] - t0) & 0xffffffff) for e in ev if (e[0], e[1]) == key])
     ts = [t for _, t in rows]
