@@ -8,6 +8,7 @@
 
 #include "common.h"
 #include "conv_gemm.cuh"
+#include "ptx.cuh"
 
 namespace cgs {
 
@@ -46,13 +47,17 @@ __device__ __forceinline__ float epilogue1(const EdgeEpi& e, float a, float x0, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// edge_wide: M = B*OH*OW output pixels, N = 64, K = k*k*cimg gathered from the pitched image through L1.
-// CTA = 4 warps, each 32 pixels x 64 channels per tile (2 x 8 mma tiles per k-step); weights live in shared
-// memory in fragment order, so a B fragment is one conflict-free LDS.64.
+// edge_wide: per tile (image b, band of RO output rows <= 256 pixels) the input rows the band needs are staged in
+// shared memory by cp.async (rows outside the image zero-filled), double-buffered so the next tile's rows arrive
+// while this tile computes; the im2col gather of the A fragments is then plain LDS with no bounds tests.
+// N = 64, K = k*k*cimg.  CTA = 8 warps; a warp takes 16 pixels x 64 channels at a time (8 mma tiles per k-step,
+// 32 accumulator registers) so that four CTAs fit an SM: the kernel is latency bound, warps in flight are what
+// buys bandwidth.  Weights live in shared memory in fragment order (one LDS.64 per B fragment).
 // ---------------------------------------------------------------------------------------------
-constexpr int EW_THREADS = 128;
+constexpr int EW_THREADS = 256;
 constexpr int EW_NT = 8;            // N = 64
 constexpr int EW_KMAX = 104;        // k <= 5, cimg <= 4
+constexpr int EW_TILE_PX = EW_THREADS;   // 32 pixels per warp
 
 // Epilogue modes compiled into the kernel (the per-element code must stay a handful of instructions: it runs 64
 // times per thread and tile): slope-type forward / derivative, the policy step, and a generic fallback (tanh, raw).
@@ -73,26 +78,32 @@ __device__ __forceinline__ float epi_fast(const EdgeEpi& e, float a, float x0, f
 }
 
 template <int MODE, bool ROUND>
-__global__ void __launch_bounds__(EW_THREADS) edge_wide_kernel(const EdgeWideParams p, int ksteps, int ntiles,
-                                                               unsigned long long fd_img, unsigned long long fd_ow) {
-  extern __shared__ float2 ew_bfrag[];   // [ksteps][8][32]
+__global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWideParams p, int ksteps, int ntiles, int RO,
+                                                                  int bands, unsigned long long fd_bands,
+                                                                  unsigned long long fd_ow) {
+  extern __shared__ float4 ew_smem4[];
+  const int PR = 2 * RO + p.k - 2;           // staged input rows per band
+  const int patch_px = PR * p.pitch;         // pixels (float4) per patch buffer
+  float2* bfrag = reinterpret_cast<float2*>(ew_smem4);                          // [ksteps][8][32]
+  float4* patch4 = ew_smem4 + ksteps * EW_NT * 32 / 2;                          // [2][PR][pitch]
   __shared__ int koff_s[EW_KMAX];
-  __shared__ int kdy_s[EW_KMAX];
+  __shared__ float bias_s[EW_NT * 8];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int kreal = p.k * p.k * p.cimg;
+  const int CI = p.cimg;
+  const int kreal = p.k * p.k * CI;
+  const int prow = p.pitch * 4;              // floats per staged row
   for (int kk = tid; kk < ksteps * 8; kk += EW_THREADS) {
-    int off = 0, dy = 1 << 20;                 // padding k entries never pass the row test
+    int off = 0;                             // padding k slots read a valid word and multiply a zero weight
     if (kk < kreal) {
-      const int tap = kk / p.cimg, c = kk - tap * p.cimg;
+      const int tap = kk / CI, c = kk - tap * CI;
       const int ky = tap / p.k, kx = tap - ky * p.k;
-      off = ((ky - p.pad_y) * p.pitch + (kx - p.pad_x + p.xoff)) * 4 + c;
-      dy = ky - p.pad_y;
+      off = ky * prow + (kx - p.pad_x + p.xoff) * 4 + c;
     }
     koff_s[kk] = off;
-    kdy_s[kk] = dy;
   }
+  if (tid < EW_NT * 8) bias_s[tid] = (p.e.epi == EPI_FWD && p.e.bias && tid < p.N) ? __ldg(p.e.bias + tid) : 0.f;
   for (int idx = tid; idx < ksteps * EW_NT * 32; idx += EW_THREADS) {
     const int l = idx & 31, nt = (idx >> 5) % EW_NT, ks = idx / (EW_NT * 32);
     const int n = nt * 8 + (l >> 2);
@@ -102,109 +113,114 @@ __global__ void __launch_bounds__(EW_THREADS) edge_wide_kernel(const EdgeWidePar
       const int kk = ks * 8 + (l & 3) + 4 * h;
       b[h] = 0.f;
       if (kk < kreal && n < p.N) {
-        const int tap = kk / p.cimg, c = kk - tap * p.cimg;
+        const int tap = kk / CI, c = kk - tap * CI;
         const int ky = tap / p.k, kx = tap - ky * p.k;
         b[h] = __ldg(p.w + (size_t)n * (p.k * 32) + ky * 32 + kx * 4 + c);
       }
     }
-    ew_bfrag[idx] = make_float2(b[0], b[1]);
+    bfrag[idx] = make_float2(b[0], b[1]);
   }
-  float2 bias2[EW_NT];
-#pragma unroll
-  for (int nt = 0; nt < EW_NT; ++nt)
-    bias2[nt] = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float2*>(p.e.bias + nt * 8 + 2 * t))
-                                                 : make_float2(0.f, 0.f);
-  __syncthreads();
 
-  const int per_img = p.OH * p.OW;
-  const int M = (int)p.M;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // the four pixels (rows of the two m16 tiles) this thread gathers for and stores
-    int base[4], y0[4], mrow[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int m = tile * 128 + warp * 32 + (r >> 1) * 16 + (r & 1) * 8 + g;
-      mrow[r] = m;
-      if (m < M) {
-        const int b = fast_div(m, fd_img);
-        const int q = m - b * per_img;
-        const int oy = fast_div(q, fd_ow), ox = q - oy * p.OW;
-        base[r] = ((b * p.IH + 2 * oy) * p.pitch + 2 * ox) * 4;
-        y0[r] = 2 * oy;
-      } else {
-        base[r] = 0;
-        y0[r] = -(1 << 21);
-      }
+  // async copy of the input rows of one tile into patch buffer `buf`
+  auto stage_patch = [&](int tile, int buf) {
+    const int b = fast_div(tile, fd_bands);
+    const int iy0 = 2 * (tile - b * bands) * RO - p.pad_y;       // image row of staged row 0
+    const uint32_t dst0 = smem_u32(patch4 + buf * patch_px);
+    for (int pr = warp; pr < PR; pr += EW_THREADS / 32) {
+      const int iy = iy0 + pr;
+      const bool ok = (unsigned)iy < (unsigned)p.IH;
+      const float4* src = reinterpret_cast<const float4*>(p.in) + (size_t)(b * p.IH + (ok ? iy : 0)) * p.pitch;
+      for (int x = lane; x < p.pitch; x += 32)
+        cp_async_16(dst0 + (pr * p.pitch + x) * 16, src + x, ok ? 16u : 0u);
     }
-    float acc[2][EW_NT][4];
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage_patch(tile, 0);
+  cp_async_commit();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const int b = fast_div(tile, fd_bands);
+    const int oy0 = (tile - b * bands) * RO;
+    const int npx = min(RO, p.OH - oy0) * p.OW;
+    const int m0 = (b * p.OH + oy0) * p.OW;                      // first output pixel of the band
+    if (tile + (int)gridDim.x < ntiles) stage_patch(tile + gridDim.x, cur ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();                      // this tile's input rows have landed
+    __syncthreads();
+    const float* patch = reinterpret_cast<const float*>(patch4 + cur * patch_px);
+    for (int mt = warp; mt * 16 < npx; mt += EW_THREADS / 32) {
+      // the two pixels (rows g, g+8 of the m16 tile) this thread gathers for and stores
+      int base[2], mloc[2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+      for (int h = 0; h < 2; ++h) {
+        const int ml = mt * 16 + h * 8 + g;
+        const int oyr = fast_div(ml, fd_ow), ox = ml - oyr * p.OW;
+        const bool ok = ml < npx;
+        base[h] = ok ? (2 * oyr * prow + 2 * ox * 4) : 0;
+        mloc[h] = ok ? ml : -1;
+      }
+      float acc[EW_NT][4];
 #pragma unroll
       for (int nt = 0; nt < EW_NT; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 #pragma unroll 2
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const int o0 = koff_s[ks * 8 + t], d0 = kdy_s[ks * 8 + t];
-      const int o1 = koff_s[ks * 8 + t + 4], d1 = kdy_s[ks * 8 + t + 4];
-      uint32_t a[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = mt * 2 + h;
-          const bool v0 = (unsigned)(y0[r] + d0) < (unsigned)p.IH;
-          const bool v1 = (unsigned)(y0[r] + d1) < (unsigned)p.IH;
-          a[mt][h] = v0 ? __float_as_uint(__ldg(p.in + base[r] + o0)) : 0u;
-          a[mt][2 + h] = v1 ? __float_as_uint(__ldg(p.in + base[r] + o1)) : 0u;
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < EW_NT; ++nt) {
-        const float2 b = ew_bfrag[(ks * EW_NT + nt) * 32 + lane];
-        mma_tf32(acc[0][nt], a[0][0], a[0][1], a[0][2], a[0][3], __float_as_uint(b.x), __float_as_uint(b.y));
-        mma_tf32(acc[1][nt], a[1][0], a[1][1], a[1][2], a[1][3], __float_as_uint(b.x), __float_as_uint(b.y));
-      }
-    }
-    // epilogue: thread owns columns nt*8 + 2t, +1 of its four rows; a quad writes one 32-byte sector
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (mrow[r] >= M) continue;
-      const int mt = r >> 1, h = r & 1;
-      float* orow = p.out + (size_t)mrow[r] * p.ON + 2 * t;
-      float2 x0[EW_NT], x1[EW_NT];
-      if (MODE == EM_FWD_SLOPE) {
-#pragma unroll
-        for (int nt = 0; nt < EW_NT; ++nt) x0[nt] = bias2[nt];
-      } else if (MODE == EM_BWD_SLOPE) {
-        const float* arow = p.e.aux + (size_t)mrow[r] * p.ON + 2 * t;
-#pragma unroll
-        for (int nt = 0; nt < EW_NT; ++nt) x0[nt] = __ldg(reinterpret_cast<const float2*>(arow + nt * 8));
-      } else {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int o0 = koff_s[ks * 8 + t];
+        const int o1 = koff_s[ks * 8 + t + 4];
+        const uint32_t a0 = __float_as_uint(patch[base[0] + o0]);
+        const uint32_t a1 = __float_as_uint(patch[base[1] + o0]);
+        const uint32_t a2 = __float_as_uint(patch[base[0] + o1]);
+        const uint32_t a3 = __float_as_uint(patch[base[1] + o1]);
 #pragma unroll
         for (int nt = 0; nt < EW_NT; ++nt) {
-          x0[nt] = bias2[nt];
-          x1[nt] = make_float2(0.f, 0.f);
-          if (p.e.epi == EPI_BWD) {
-            x0[nt] = __ldg(reinterpret_cast<const float2*>(p.e.aux + (size_t)mrow[r] * p.ON + 2 * t + nt * 8));
-          } else if (p.e.epi == EPI_UPDATE) {
-            x0[nt] = *reinterpret_cast<const float2*>(orow + nt * 8);
-            if (!p.e.sgd && !p.e.first)
-              x1[nt] = *reinterpret_cast<const float2*>(p.e.mom + (size_t)mrow[r] * p.ON + 2 * t + nt * 8);
+          const float2 bq = bfrag[(ks * EW_NT + nt) * 32 + lane];
+          mma_tf32(acc[nt], a0, a1, a2, a3, __float_as_uint(bq.x), __float_as_uint(bq.y));
+        }
+      }
+      // epilogue: thread owns columns nt*8 + 2t, +1 of its two rows; a quad writes one 32-byte sector
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (mloc[h] < 0) continue;
+        const size_t ro = (size_t)(m0 + mloc[h]) * p.ON + 2 * t;
+        float* orow = p.out + ro;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float2 x0[EW_NT / 2], x1[EW_NT / 2];
+#pragma unroll
+          for (int q = 0; q < EW_NT / 2; ++q) {
+            const int nt = half * (EW_NT / 2) + q;
+            x1[q] = make_float2(0.f, 0.f);
+            if (MODE == EM_FWD_SLOPE) {
+              x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
+            } else if (MODE == EM_BWD_SLOPE) {
+              x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
+            } else {
+              x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
+              if (p.e.epi == EPI_BWD) {
+                x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
+              } else if (p.e.epi == EPI_UPDATE) {
+                x0[q] = *reinterpret_cast<const float2*>(orow + nt * 8);
+                if (!p.e.sgd && !p.e.first) x1[q] = *reinterpret_cast<const float2*>(p.e.mom + ro + nt * 8);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < EW_NT / 2; ++q) {
+            const int nt = half * (EW_NT / 2) + q;
+            float2 m2 = make_float2(0.f, 0.f), o;
+            o.x = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h], x0[q].x, x1[q].x, &m2.x);
+            o.y = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h + 1], x0[q].y, x1[q].y, &m2.y);
+            if (MODE >= EM_UPDATE && p.e.epi == EPI_UPDATE && !p.e.sgd) *reinterpret_cast<float2*>(p.e.mom + ro + nt * 8) = m2;
+            *reinterpret_cast<float2*>(orow + nt * 8) = o;
           }
         }
       }
-#pragma unroll
-      for (int nt = 0; nt < EW_NT; ++nt) {
-        float2 m2 = make_float2(0.f, 0.f), o;
-        o.x = epi_fast<MODE, ROUND>(p.e, acc[mt][nt][2 * h], x0[nt].x, x1[nt].x, &m2.x);
-        o.y = epi_fast<MODE, ROUND>(p.e, acc[mt][nt][2 * h + 1], x0[nt].y, x1[nt].y, &m2.y);
-        if (MODE >= EM_UPDATE && p.e.epi == EPI_UPDATE && !p.e.sgd)
-          *reinterpret_cast<float2*>(p.e.mom + (size_t)mrow[r] * p.ON + 2 * t + nt * 8) = m2;
-        *reinterpret_cast<float2*>(orow + nt * 8) = o;
-      }
     }
+    __syncthreads();                         // patch[cur] may be overwritten from here on
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -369,36 +385,45 @@ bool edge_narrow_supported(int K, int k, int cimg, int IW) {
 }
 
 template <int MODE, bool ROUND>
-int launch_wide_mode(const EdgeWideParams& p, int ksteps, int tiles, cudaStream_t st) {
-  const size_t smem = (size_t)ksteps * EW_NT * 32 * sizeof(float2);
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, edge_wide_kernel<MODE, ROUND>, EW_THREADS,
-                                                                  (size_t)13 * EW_NT * 32 * sizeof(float2));
-    if (e != cudaSuccess || n < 1) return set_error(CGS_ERR_CUDA, "edge_wide occupancy query failed");
-    ctas_per_sm = n;
+int launch_wide_mode(const EdgeWideParams& p, int B, cudaStream_t st) {
+  const int ksteps = (p.k * p.k * p.cimg + 7) / 8;
+  const int RO = (p.OH * p.OW <= EW_TILE_PX) ? p.OH : EW_TILE_PX / p.OW;   // whole image per tile when it fits
+  const int bands = (p.OH + RO - 1) / RO;
+  const long long tiles_ll = (long long)B * bands;
+  if (tiles_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large; split the batch");
+  const int tiles = (int)tiles_ll;
+  const int PR = 2 * RO + p.k - 2;
+  size_t smem = (size_t)ksteps * EW_NT * 32 * sizeof(float2) + (size_t)2 * PR * p.pitch * sizeof(float4);
+  if (smem > 200 * 1024) return set_error(CGS_ERR_UNSUPPORTED, "edge_wide: image band does not fit shared memory");
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(edge_wide_kernel<MODE, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_wide): %s", cudaGetErrorString(e));
+    smem_set = smem;
   }
-  int grid = num_sms() * ctas_per_sm;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_wide_kernel<MODE, ROUND>, EW_THREADS, smem);
+  if (e != cudaSuccess || per_sm < 1) return set_error(CGS_ERR_CUDA, "edge_wide occupancy query failed");
+  long long grid = (long long)num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
-  edge_wide_kernel<MODE, ROUND><<<grid, EW_THREADS, smem, st>>>(p, ksteps, tiles, fast_div_magic((unsigned)(p.OH * p.OW)),
-                                                                  fast_div_magic((unsigned)p.OW));
+  edge_wide_kernel<MODE, ROUND><<<(int)grid, EW_THREADS, smem, st>>>(p, ksteps, tiles, RO, bands, fast_div_magic((unsigned)bands),
+                                                                       fast_div_magic((unsigned)p.OW));
   count_launch();
   return check_launch("edge_wide_kernel");
 }
 
 int launch_edge_wide(const EdgeWideParams& p, cudaStream_t st) {
   if (p.M <= 0) return CGS_OK;
-  const int ksteps = (p.k * p.k * p.cimg + 7) / 8;
   if (p.M * p.ON >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit indexing; split the batch");
-  const int tiles = (int)((p.M + 127) / 128);
+  if (p.OW > EW_TILE_PX) return set_error(CGS_ERR_UNSUPPORTED, "edge_wide: output row wider than a tile");
+  const int B = (int)(p.M / ((long long)p.OH * p.OW));
   const bool rnd = p.e.round_out != 0;
   if (p.e.epi == EPI_FWD && !p.e.act_tanh)
-    return rnd ? launch_wide_mode<EM_FWD_SLOPE, true>(p, ksteps, tiles, st) : launch_wide_mode<EM_FWD_SLOPE, false>(p, ksteps, tiles, st);
+    return rnd ? launch_wide_mode<EM_FWD_SLOPE, true>(p, B, st) : launch_wide_mode<EM_FWD_SLOPE, false>(p, B, st);
   if (p.e.epi == EPI_BWD && !p.e.act_tanh)
-    return rnd ? launch_wide_mode<EM_BWD_SLOPE, true>(p, ksteps, tiles, st) : launch_wide_mode<EM_BWD_SLOPE, false>(p, ksteps, tiles, st);
-  if (p.e.epi == EPI_UPDATE) return launch_wide_mode<EM_UPDATE, false>(p, ksteps, tiles, st);
-  return launch_wide_mode<EM_GENERIC, false>(p, ksteps, tiles, st);
+    return rnd ? launch_wide_mode<EM_BWD_SLOPE, true>(p, B, st) : launch_wide_mode<EM_BWD_SLOPE, false>(p, B, st);
+  if (p.e.epi == EPI_UPDATE) return launch_wide_mode<EM_UPDATE, false>(p, B, st);
+  return launch_wide_mode<EM_GENERIC, false>(p, B, st);
 }
 
 int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
