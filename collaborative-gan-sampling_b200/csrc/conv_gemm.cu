@@ -25,12 +25,16 @@ namespace cgs {
 __device__ unsigned long long g_trace[32768];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ void trace(const ConvGemmParams& p, int role, int ev, unsigned idx) {
+#ifdef CGS_TRACE
   // fixed slot per (role, event, index): a plain store, no atomics, so the traced thread is barely perturbed
   if ((p.debug & 256) && blockIdx.x == 0 && idx < 1024) {
     const unsigned slot = ((unsigned)(role * 4 + ev) << 10) + idx;
     g_trace[slot & 32767] = ((unsigned long long)role << 60) | ((unsigned long long)ev << 56) |
                             ((unsigned long long)(idx & 0xffffff) << 32) | (unsigned long long)(unsigned)clock64();
   }
+#else
+  (void)p; (void)role; (void)ev; (void)idx;      // build with CGS_NVCC_EXTRA=-DCGS_TRACE to record the trace
+#endif
 }
 
 namespace {
@@ -210,6 +214,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // {32, rows, K/32} so ONE box {32, BN, KB} fetches all K atoms of a stage as consecutive atom tiles.
     const uint32_t smem_b_u32 = smem_u32(smem_b);
     uint32_t it_global = 0;
+    uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ci = fast_div(tile, p.fd_tiles_per_class);
       const int rem = tile - ci * tiles_per_class;
@@ -217,8 +222,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const int katom0 = p.cls[ci].k0 / BK;
       const int nkb = p.cls[ci].nkb;
       for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
-        const int s = it_global % C::STAGES;
-        const uint32_t ph = (it_global / C::STAGES) & 1;
+        const uint32_t s = stage, ph = phase;
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           trace(p, 1, 0, it_global);
@@ -237,7 +242,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     if (p.a_tma) {
       const uint32_t smem_a_u32 = smem_u32(smem_a);
       const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
-      uint32_t it_global = 0;
+      uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ci = fast_div(tile, p.fd_tiles_per_class);
         const int rem = tile - ci * tiles_per_class;
@@ -248,13 +253,13 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const int b0 = mb * p.BB;
         const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
         int t = 0, cb = 0;
-        for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
-          const int s = it_global % C::STAGES;
-          const uint32_t ph = (it_global / C::STAGES) & 1;
+        for (int kb = 0; kb < nkb; kb += C::KB) {
+          const uint32_t s = stage, ph = phase;
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
           const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (elect_one()) {
-            if (p.debug & 2) {
+            if (p.debug & 8) {
               mbar_arrive(&full_bar[s]);
             } else {
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * a_bytes);
@@ -287,30 +292,37 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
     const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem_a));
     const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem_b));
+    // The loop body is kept minimal (ring position kept incrementally, parameters hoisted, no trace code unless
+    // built with CGS_TRACE): the issuing thread runs in lock-step with the tensor pipe, so every instruction here is
+    // a bubble between K blocks.  Releasing a stage one K block late (commit after the next block's MMAs) was
+    // measured and is slower: ring depth (3-4 stages) matters more than the issue bubble.
     uint32_t it_global = 0;
     uint32_t tile_count = 0;
+    uint32_t stage = 0, phase = 0;               // position in the smem ring
+    const bool a_tma = p.a_tma != 0;
+    const bool skip_mma = (p.debug & 4) != 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
       const int ci = fast_div(tile, p.fd_tiles_per_class);
       const int nkb = p.cls[ci].nkb;
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
-      tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
-        const int s = it_global % C::STAGES;
-        const uint32_t ph = (it_global / C::STAGES) & 1;
+        const uint32_t s = stage;
         const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;
-        mbar_wait(&full_bar[s], ph);
+        const bool last = kb + C::KB >= nkb;
+        mbar_wait(&full_bar[s], phase);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         tcgen05_fence_after();
         if (elect_one()) {
           trace(p, 2, 0, it_global);
           // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-          if (!p.a_tma) fence_proxy_async_smem();
+          if (!a_tma) fence_proxy_async_smem();
           // descriptor address field is in 16-byte units: + stage / atom offset, + 32 bytes per K=8 step
           const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
           const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
-          if (!(p.debug & 4)) {
+          if (!skip_mma) {
 #pragma unroll
             for (int a = 0; a < C::KB; ++a) {
               if (a >= na) break;
@@ -321,10 +333,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             }
           }
           umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
-          if (kb + C::KB >= nkb) umma_commit(&tmem_full_bar[acc]);   // accumulator complete
+          if (last) umma_commit(&tmem_full_bar[acc]);            // accumulator complete
           trace(p, 2, 1, it_global);
         }
-        __syncwarp();
       }
     }
   } else {
@@ -703,7 +714,13 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  switch (pick_bn_for(p, num_sms)) {
+  int bn = pick_bn_for(p, num_sms);
+  {
+    static int force = -1;                    // developer knob: CGS_FORCE_BN=16..256 overrides the tile-width heuristic
+    if (force < 0) { const char* e = getenv("CGS_FORCE_BN"); force = e ? atoi(e) : 0; }
+    if (force) bn = force;
+  }
+  switch (bn) {
     case 16: return launch_tc<16>(p, w, w_rows, w_cols, stream);
     case 32: return launch_tc<32>(p, w, w_rows, w_cols, stream);
     case 64: return launch_tc<64>(p, w, w_rows, w_cols, stream);

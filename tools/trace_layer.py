@@ -45,6 +45,7 @@ ev = [(int(v >> 60), int((v >> 56) & 0xf), int((v >> 32) & 0xffffff), int(v & 0x
 t0 = min(e[3] for e in ev)
 names = {(0, 0): "P.wait_empty", (0, 1): "P.issued", (1, 0): "T.wait_empty", (2, 0): "M.wait_full", (2, 1): "M.commit",
          (2, 2): "M.tmem_empty", (3, 0): "E.tmem_full", (3, 1): "E.released", (3, 2): "E.done",
+         (5, 0): "M5.loop_top", (5, 1): "M5.waited", (5, 3): "M5.mma_issued", (5, 2): "M5.loop_end",
          (4, 0): "C.ld_done", (4, 1): "C.math_done", (4, 2): "C.stored", (4, 3): "C.synced"}
 print("events", len(ev))
 chunk = {}
