@@ -185,7 +185,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             if (!tap_ok) tt = 31;         // bit 31 is never set (ntaps <= 25)
           } else {
             tt = t;
-            off = tap_off + cb * BK + chunk * 4;
+            off = tap_off + (cb + gc.cb0) * BK + chunk * 4;
           }
           const uint32_t atom_base = smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES;
           if (!(p.debug & 1)) {
@@ -268,8 +268,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
               for (int a = 0; a < C::KB; ++a) {
                 if (a >= na) break;
                 // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
-                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s], cc * BK,
-                            gc.dx[tt], y_tile + gc.dy[tt], b0);
+                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s],
+                            (cc + gc.cb0) * BK, gc.dx[tt], y_tile + gc.dy[tt], b0);
                 if (++cc == p.cblocks) {
                   cc = 0;
                   ++tt;
@@ -520,7 +520,7 @@ conv_gemm_simt_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
       const float* src = p.in + ((size_t)(b * p.IH + y) * p.IW + x) * p.Cs;
       for (int c = 0; c < cin; ++c) {
         const float a = __ldg(src + c);
-        const int k = gc.k0 + tp * cin + c;
+        const int k = gc.k0 + tp * cin + c;             // (split-K classes are a tensor-core-path lowering only)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int n = ng * 4 + u;
@@ -714,7 +714,7 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  int bn = pick_bn_for(p, num_sms);
+  int bn = p.force_bn ? p.force_bn : pick_bn_for(p, num_sms);
   {
     static int force = -1;                    // developer knob: CGS_FORCE_BN=16..256 overrides the tile-width heuristic
     if (force < 0) { const char* e = getenv("CGS_FORCE_BN"); force = e ? atoi(e) : 0; }

@@ -33,6 +33,7 @@ struct GemmClass {
   int ntaps;   // taps of this class = nky * nkx, tap t = ty * nkx + tx, dy depends on ty only, dx on tx only
   int nkx;
   int oy0, ox0;
+  int cb0;     // first 32-channel block of the A operand read by this class (split-K classes of an fc layer)
   signed char dy[kMaxTaps];
   signed char dx[kMaxTaps];
 };
@@ -66,6 +67,7 @@ struct ConvGemmParams {
   float slope;        // derived from act by the launcher: relu 0, lrelu 0.2, none 1 (branch-free epilogue)
   int act_tanh;       // act == tanh (slow path)
   int round_out;      // round results to TF32 (RN) because the next consumer is a kind::tf32 MMA
+  int force_bn;       // 0 = tile-width heuristic, else the BN instance to launch
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
   // exact division of the persistent tile index by multiply-shift (filled by the launcher; see fast_div)
   unsigned long long fd_tiles_per_class, fd_n_tiles, fd_hy_tiles;

@@ -4,6 +4,7 @@
 #include "conv_gemm.cuh"
 #include "edge_conv.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace cgs {
@@ -300,7 +301,20 @@ bool use_scatter(const cgs_layer_desc& L, bool backward) {
 }
 inline int scatter_cols(const cgs_layer_desc& L) { return L.k * L.k * 4; }      // col row pitch (floats)
 
-size_t scatter_col_elems(const cgs_layer_desc& L, bool backward) {
+// Split-K for the forward pass of a long-K fc layer (d_fc3: 6272 -> 1024): at batch 1024 there are only 8 x 4 tiles of
+// 128 x 256, and a CTA pays one pipeline hand-shake per K block whatever the tile width, so narrow tiles over the full
+// K (128 tiles of 128 x 64, 98 K blocks each) run at a third of the wide-tile rate.  Instead: 128 x 256 tiles over a
+// quarter of K each (the split is a "class" of the gathered GEMM: own K range, own output row), FP32 partial sums in
+// the pass scratch buffer, and a small kernel that adds the four partials in a fixed order and applies the epilogue.
+constexpr int kFcSplit = 4;
+inline int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+inline int fc_split(const cgs_layer_desc& L, bool backward) {
+  static const int S = env_int("CGS_FC_SPLIT", kFcSplit);      // developer knob
+  return (L.type == CGS_LAYER_FC && !backward && L.cin >= 4096 && L.cin % (32 * S) == 0) ? S : 1;
+}
+
+size_t scatter_col_elems(const cgs_layer_desc& L, bool backward) {     // per-sample elements of the pass scratch buffer
+  if (fc_split(L, backward) > 1) return (size_t)fc_split(L, backward) * cstride(L.cout);
   if (!use_scatter(L, backward)) return 0;
   const LayerShape s = layer_shape(L);
   const size_t pixels = backward ? (size_t)s.hout * s.wout : (size_t)L.hin * L.win;   // stage-1 rows per sample
@@ -426,6 +440,41 @@ int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int
   return set_error(CGS_ERR_INVALID, "unknown math mode %d", math);
 }
 
+// out[b][n] = epi( part[b][0][n] + part[b][1][n] + ... ) in a fixed order; same epilogue code as the GEMM kernels
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ ConvGemmParams p,
+                                                            const float* __restrict__ part, int S, long long total4) {
+  const int groups = p.ON / 4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / groups;
+    const int ng = (int)(idx - b * groups);
+    const int off = (int)(b * p.ON) + ng * 4;
+    float4 a = __ldg(reinterpret_cast<const float4*>(part + (size_t)b * S * p.ON + ng * 4));
+    for (int s = 1; s < S; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + ((size_t)b * S + s) * p.ON + ng * 4));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (p.epi == EPI_FWD) { if (p.bias) x0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng * 4)); }
+    else if (p.epi == EPI_BWD) x0 = __ldg(reinterpret_cast<const float4*>(p.aux + off));
+    else if (p.epi == EPI_UPDATE) {
+      x0 = *reinterpret_cast<const float4*>(p.out + off);
+      if (!p.sgd && !p.first) x1 = *reinterpret_cast<const float4*>(p.mom + off);
+    }
+    *reinterpret_cast<float4*>(p.out + off) = epilogue4(p, off, a, x0, x1);
+  }
+}
+
+int launch_splitk_reduce(ConvGemmParams pe, const float* part, int S, int64_t B, cudaStream_t st) {
+  pe.act_tanh = (pe.act == ACT_TANH);
+  pe.slope = pe.act == ACT_RELU ? 0.f : (pe.act == ACT_LRELU ? 0.2f : 1.f);
+  const long long total4 = (long long)B * (pe.ON / 4);
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(pe, part, S, total4); count_launch();
+  return check_launch("splitk_reduce_kernel");
+}
+
 // One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
 int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
              float* col, int math, cudaStream_t st, bool dense_image = false) {
@@ -489,6 +538,38 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     return check_launch("col2im_kernel");
   }
   ConvGemmParams p;
+  if (const int S = fc_split(L, backward); S > 1 && math == CGS_MATH_TF32_TENSOR && col && !(debug_flags() & 16384) &&
+                                           ((B + 127) / 128) * ((L.cout + 255) / 256) * S <= 2 * 148) {
+    if (int rc = make_forward_params(L, B, in, col, p)) return rc;
+    ConvGemmParams pe = p;                    // epilogue description of the real output
+    pe.out = out;
+    pe.bias = L.bias;
+    pe.epi = e.epi; pe.act = e.act; pe.aux = e.aux; pe.round_out = e.round_out;
+    if (e.upd) {
+      pe.epi = EPI_UPDATE;
+      pe.mom = e.upd->mom; pe.first = e.upd->first; pe.sgd = e.upd->sgd; pe.rate = e.upd->rate; pe.alpha = e.upd->alpha;
+      pe.clip = e.upd->clip; pe.vmin = e.upd->vmin; pe.vmax = e.upd->vmax;
+      pe.round_out = 0;
+    }
+    p.bias = nullptr;
+    p.epi = EPI_RAW;
+    p.nclasses = S;
+    p.cblocks = L.cin / 32 / S;
+    for (int c = 0; c < S; ++c) {
+      GemmClass& g = p.cls[c];
+      std::memset(&g, 0, sizeof(g));
+      g.k0 = c * p.cblocks * 32;
+      g.nkb = p.cblocks;
+      g.ntaps = 1;
+      g.nkx = 1;
+      g.oy0 = c;                              // partial sums of split c land in row (b * S + c) of the scratch buffer
+      g.cb0 = c * p.cblocks;
+    }
+    p.OH = S;
+    { static const int bn = env_int("CGS_FC_BN", 256); p.force_bn = bn; }
+    if (int rc = launch_gemm(p, w, rows, cols, math, st)) return rc;
+    return launch_splitk_reduce(pe, col, S, B, st);
+  }
   if (use_window(L, backward)) {
     if (rows != (backward ? L.cin : L.cout) || cols != window_kcols(L))
       return set_error(CGS_ERR_INVALID, "weights of this pass must be in window layout (%d columns)", window_kcols(L));
@@ -1018,7 +1099,7 @@ static int layer_pass_dense(const cgs_layer_desc& L, bool backward, int math, in
   if (needs_ws && (!workspace || workspace_bytes < cgs_layer_workspace_bytes(&L, B)))
     return set_error(CGS_ERR_WORKSPACE, "workspace too small");
   float* base = (float*)(((uintptr_t)workspace + 255) & ~uintptr_t(255));
-  float* col = base;
+  float* col = (workspace && workspace_bytes >= cgs_layer_workspace_bytes(&L, B)) ? base : nullptr;
   size_t ce = scatter_col_elems(L, false);
   if (scatter_col_elems(L, true) > ce) ce = scatter_col_elems(L, true);
   float* stage = base + ((ce * (size_t)B + 63) & ~size_t(63));
