@@ -296,8 +296,8 @@ def measure_extra(torch, name, dev, math, steps=2, warmup=1):
            "peak_note": "0.5 x MEASURED_PEAKS bf16_tflops_sustained (whole-step number, kernel timed inside a long step)"}
     tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get("dcgan64")
-        if tj:
+        tj = (json.load(open(tpath)).get("dcgan64") or {}).get("conv_gemm_tc")
+        if tj:                                # ncu, conv_gemm_tc launches of one step pair, time-weighted
             out["ncu_tensor_pipe_active_pct"] = tj["tensor_pipe_active_pct_time_weighted"]
     del refiner, spec
     torch.cuda.empty_cache()

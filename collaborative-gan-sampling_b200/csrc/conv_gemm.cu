@@ -115,6 +115,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // set-up done: let the next kernel of the chain start its own set-up, then wait for our predecessor's results
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_class = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_per_class * p.nclasses;
@@ -668,8 +671,9 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
   p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p, tmap, tmap_a); count_launch();
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
+  count_launch();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
 }

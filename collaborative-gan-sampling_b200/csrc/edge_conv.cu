@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWide
     }
   };
 
+  pdl_launch_dependents();
+  pdl_wait();                                // tables and weights above are constants; activations from here on
   int tile = blockIdx.x;
   if (tile < ntiles) stage_patch(tile, 0);
   cp_async_commit();
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarro
     bfrag[idx] = b;
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();                                // weights above are constants; activations from here on
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = tile / p.bands;
@@ -369,8 +373,9 @@ int launch_narrow_nt(const EdgeNarrowParams& p, cudaStream_t st) {
   if (tiles >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large; split the batch");
   long long grid = (long long)num_sms() * ctas_per_sm;
   if (grid > tiles) grid = tiles;
-  edge_narrow_kernel<NT, CI><<<(int)grid, EN_THREADS, smem, st>>>(p, (int)tiles);
+  cudaError_t le = launch_pdl(edge_narrow_kernel<NT, CI>, dim3((unsigned)grid), dim3(EN_THREADS), smem, st, p, (int)tiles);
   count_launch();
+  if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_narrow_kernel: %s", cudaGetErrorString(le));
   return check_launch("edge_narrow_kernel");
 }
 
@@ -406,9 +411,10 @@ int launch_wide_mode(const EdgeWideParams& p, int B, cudaStream_t st) {
   if (e != cudaSuccess || per_sm < 1) return set_error(CGS_ERR_CUDA, "edge_wide occupancy query failed");
   long long grid = (long long)num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
-  edge_wide_kernel<MODE, ROUND><<<(int)grid, EW_THREADS, smem, st>>>(p, ksteps, tiles, RO, bands, fast_div_magic((unsigned)bands),
-                                                                       fast_div_magic((unsigned)p.OW));
+  cudaError_t le = launch_pdl(edge_wide_kernel<MODE, ROUND>, dim3((unsigned)grid), dim3(EW_THREADS), smem, st, p, ksteps, tiles, RO,
+                              bands, fast_div_magic((unsigned)bands), fast_div_magic((unsigned)p.OW));
   count_launch();
+  if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_wide_kernel: %s", cudaGetErrorString(le));
   return check_launch("edge_wide_kernel");
 }
 

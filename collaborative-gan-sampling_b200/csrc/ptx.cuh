@@ -76,6 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 #endif
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Opt-in (common.h launch_pdl): with programmatic stream serialization a kernel's set-up (barrier init, TMEM
+// allocation, weight staging) may run while the previous kernel drains; pdl_wait() returns once the previous kernel
+// has completed and its writes are visible, and precedes every access to activation memory.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / cp.async
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -3,6 +3,7 @@
 #include "common.h"
 #include "conv_gemm.cuh"
 #include "edge_conv.cuh"
+#include "ptx.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -443,6 +444,8 @@ int launch_gemm(const ConvGemmParams& p, const float* w, int rows, int cols, int
 // out[b][n] = epi( part[b][0][n] + part[b][1][n] + ... ) in a fixed order; same epilogue code as the GEMM kernels
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ ConvGemmParams p,
                                                             const float* __restrict__ part, int S, long long total4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = p.ON / 4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -471,7 +474,9 @@ int launch_splitk_reduce(ConvGemmParams pe, const float* part, int S, int64_t B,
   const long long total4 = (long long)B * (pe.ON / 4);
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(pe, part, S, total4); count_launch();
+  cudaError_t le = launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, pe, part, S, total4);
+  count_launch();
+  if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "splitk_reduce_kernel: %s", cudaGetErrorString(le));
   return check_launch("splitk_reduce_kernel");
 }
 
@@ -642,6 +647,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float red[8];
   __shared__ float s_logit;
   __shared__ int s_update;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int ob = p.orig ? p.orig[b] : b;           // where this sample's results live
   const float* f = p.feat + (size_t)b * p.K;
@@ -914,7 +921,9 @@ static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams
   hp.feature = w.act[0];
   hp.feat_elems = (int)c.act_elems[0];
   hp.cur_logit = w.cur_logit;
-  head_kernel<<<(unsigned)B, 256, 0, st>>>(hp); count_launch();
+  cudaError_t le = launch_pdl(head_kernel, dim3((unsigned)B), dim3(256), (size_t)0, st, hp);
+  count_launch();
+  if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "head_kernel: %s", cudaGetErrorString(le));
   return check_launch("head_kernel");
 }
 
