@@ -1,16 +1,20 @@
 // tcgen05 / TMEM implicit-GEMM kernel (TF32 inputs, FP32 accumulate) + an FP32 SIMT twin used by the
 // parity tests and as the exact-FP32 mode.  See conv_gemm.cuh for the contraction it computes.
 //
-// CTA = 14 warps, persistent over output tiles (128 rows x BN channels):
+// CTA = 15 warps, persistent over output tiles (128 rows x BN channels):
 //   warps 0-3   epilogue: tcgen05.ld the accumulator (TMEM lane = row), transpose through padded smem so that
-//               global loads/stores are 128-byte row segments, fused bias/activation/derivative/momentum update
-//   warps 4-11  A producers: cp.async gather of 128 rows x 128 B per K block into SWIZZLE_128B smem; per tile
-//               each thread precomputes its 4 row bases + tap-validity bit masks, per K block it only adds a
-//               warp-uniform tap offset (the per-K-block instruction count, not bandwidth, bounds this role)
-//   warp  12    MMA issuer (one elected lane): 4 x tcgen05.mma.kind::tf32 (K=8 each) per K block
-//   warp  13    TMA producer for the weight tile (BN rows x 128 B, SWIZZLE_128B)
-// Pipelines: full/empty mbarriers per smem stage, tmem_full/tmem_empty per accumulator buffer
-// (2 x BN TMEM columns, so the epilogue of tile i overlaps the main loop of tile i+1).
+//               global loads/stores are 64-byte row segments, fused bias/activation/derivative/momentum update
+//   warps 4-11  TMA mode (every layer with >= 32 input channels): two more epilogue groups.  Up to BN = 128 each
+//               group owns whole tiles, at BN = 256 the three groups split one tile's 16-column chunks.
+//               Gather mode (pixel layout, <= 4 channels): A producers, cp.async gather of 128 rows x 128 B per K
+//               block into SWIZZLE_128B smem
+//   warp  12    MMA issuer (one elected lane of a warp-uniform loop): 4 x tcgen05.mma.kind::tf32 (K=8) per K atom
+//   warp  13    TMA producer for the weight tile (one 3-D box {32, BN, KB} per stage, SWIZZLE_128B)
+//   warp  14    TMA producer for the A tile (one 4-D box per K atom with traversal strides, or the window map)
+// Pipelines: full/empty mbarriers per smem stage (3-8 stages, 1-2 K atoms each), tmem_full/tmem_empty per
+// accumulator buffer (ring of 4 x BN TMEM columns, 2 at BN = 256: tile epilogues overlap the following main loops).
+// CGS_DEBUG knobs (cgs_debug_set_flags): 1 skip A gather, 2 skip weight TMA, 8 skip A TMA, 4 skip MMA issue,
+// 16 skip epilogue work, 512 force gather mode, 1024 skip stores, 2048 no operand prefetch, 256 event trace (CGS_TRACE).
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 #include "common.h"

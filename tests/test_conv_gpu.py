@@ -192,6 +192,36 @@ def test_cuda_graph_replay_is_bit_identical(cgs_lib, cuda_device):
         assert torch.equal(eager.optimal_step, graph.optimal_step) and torch.equal(eager.current_feature, graph.current_feature)
 
 
+def test_launch_and_lowering_knobs_do_not_change_results(cgs_lib, cuda_device):
+    """Programmatic dependent launch (bit 32768) reorders nothing: bit-identical.  The fc split-K lowering (off with
+    bit 16384) and the fused edge kernels (off with bit 4096) only change summation order: same refined batch within
+    the TF32 tolerance and the same best step for nearly every sample."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("mnist", 5, 3.0, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(40, *arch["feature_shape"], generator=torch.Generator().manual_seed(4))).to(cuda_device)
+
+    def run(flags):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(5, 0.1)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            x = r.build_refiner(h0)
+            torch.cuda.synchronize()
+            return x.clone(), r.optimal_logit.clone(), r.optimal_step.clone()
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    base = run(0)
+    pdl = run(32768)
+    assert all(torch.equal(a, b) for a, b in zip(base, pdl))
+    for flags in (16384, 4096, 16384 | 4096):
+        x, logit, step = run(flags)
+        assert rel_l2(x.cpu().numpy(), base[0].cpu().numpy()) <= 1e-2
+        assert float((logit - base[1]).abs().max()) <= 1.5e-2
+        assert float((step == base[2]).float().mean()) >= 0.9
+
+
 def test_mnist_layer2_and_chunked_batches(cgs_lib, cuda_device, monkeypatch):
     """Refinement at the [14,14,64] map (G-tail = last deconv only) and chunked refinement of over-size batches."""
     from cgs import nets as N
