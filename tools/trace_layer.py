@@ -1,4 +1,9 @@
-"""Run one layer pass with the CTA-0 pipeline trace on (CGS_DEBUG |= 256) and print per-role event timelines."""
+"""Run one layer pass with the CTA-0 pipeline trace on (CGS_DEBUG |= 256) and print per-role event timelines.
+
+The trace code is compiled out of the product build: rebuild first with
+    CGS_NVCC_EXTRA=-DCGS_TRACE python collaborative-gan-sampling_b200/build.py -f
+(and rebuild without it afterwards).
+"""
 import argparse
 import ctypes as C
 import os
