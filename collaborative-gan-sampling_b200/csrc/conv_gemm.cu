@@ -220,28 +220,28 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // whole warp walks the loop (uniform control flow); one elected lane issues.  The weight matrix is viewed as
     // {32, rows, K/32} so ONE box {32, BN, KB} fetches all K atoms of a stage as consecutive atom tiles.
     const uint32_t smem_b_u32 = smem_u32(smem_b);
-    uint32_t it_global = 0;
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ci = fast_div(tile, p.fd_tiles_per_class);
-      const int rem = tile - ci * tiles_per_class;
-      const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
-      const int katom0 = p.cls[ci].k0 / BK;
-      const int nkb = p.cls[ci].nkb;
-      for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
-        const uint32_t s = stage, ph = phase;
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (elect_one()) {
+    if (elect_one()) {                     // one thread walks the whole loop: no per-K-block election or warp sync
+      uint32_t it_global = 0;
+      uint32_t stage = 0, phase = 0;
+      const bool skip = (p.debug & 2) != 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ci = fast_div(tile, p.fd_tiles_per_class);
+        const int rem = tile - ci * tiles_per_class;
+        const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
+        const int katom0 = p.cls[ci].k0 / BK;
+        const int nkb = p.cls[ci].nkb;
+        for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
+          const uint32_t s = stage, ph = phase;
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          mbar_wait(&empty_bar[s], ph ^ 1);
           trace(p, 1, 0, it_global);
-          if (p.debug & 2) {
+          if (skip) {
             mbar_arrive(&full_bar[s]);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
             tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], 0, n_tile * BN, katom0 + kb);
           }
         }
-        __syncwarp();
       }
     }
   } else if (warp == kTmaWarpA) {
@@ -249,47 +249,44 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     if (p.a_tma) {
       const uint32_t smem_a_u32 = smem_u32(smem_a);
       const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ci = fast_div(tile, p.fd_tiles_per_class);
-        const int rem = tile - ci * tiles_per_class;
-        const int m_tile = fast_div(rem, p.fd_n_tiles);
-        const GemmClass& gc = p.cls[ci];
-        const int nkb = gc.nkb;
-        const int mb = fast_div(m_tile, p.fd_hy_tiles);
-        const int b0 = mb * p.BB;
-        const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
-        int t = 0, cb = 0;
-        for (int kb = 0; kb < nkb; kb += C::KB) {
-          const uint32_t s = stage, ph = phase;
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-          const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (elect_one()) {
-            if (p.debug & 8) {
+      if (elect_one()) {                   // one thread walks the whole loop
+        uint32_t stage = 0, phase = 0;
+        const bool skip = (p.debug & 8) != 0;
+        const int cblocks = p.cblocks;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int ci = fast_div(tile, p.fd_tiles_per_class);
+          const int rem = tile - ci * tiles_per_class;
+          const int m_tile = fast_div(rem, p.fd_n_tiles);
+          const GemmClass& gc = p.cls[ci];
+          const int nkb = gc.nkb;
+          const int mb = fast_div(m_tile, p.fd_hy_tiles);
+          const int b0 = mb * p.BB;
+          const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
+          const int cb0 = gc.cb0;
+          int t = 0, cb = 0;
+          for (int kb = 0; kb < nkb; kb += C::KB) {
+            const uint32_t s = stage, ph = phase;
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (skip) {
               mbar_arrive(&full_bar[s]);
             } else {
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * a_bytes);
-              int tt = t, cc = cb;
+            }
 #pragma unroll
-              for (int a = 0; a < C::KB; ++a) {
-                if (a >= na) break;
-                // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
+            for (int a = 0; a < C::KB; ++a) {
+              if (a >= na) break;
+              // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
+              if (!skip)
                 tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s],
-                            (cc + gc.cb0) * BK, gc.dx[tt], y_tile + gc.dy[tt], b0);
-                if (++cc == p.cblocks) {
-                  cc = 0;
-                  ++tt;
-                }
+                            (cb + cb0) * BK, gc.dx[t], y_tile + gc.dy[t], b0);
+              if (++cb == cblocks) {
+                cb = 0;
+                ++t;
               }
             }
           }
-          __syncwarp();
-          for (int a = 0; a < na; ++a)
-            if (++cb == p.cblocks) {
-              cb = 0;
-              ++t;
-            }
         }
       }
     }
