@@ -300,6 +300,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // built with CGS_TRACE): the issuing thread runs in lock-step with the tensor pipe, so every instruction here is
     // a bubble between K blocks.  Releasing a stage one K block late (commit after the next block's MMAs) was
     // measured and is slower: ring depth (3-4 stages) matters more than the issue bubble.
+    if (elect_one()) {                         // one thread walks the whole loop
     uint32_t it_global = 0;
     uint32_t tile_count = 0;
     uint32_t stage = 0, phase = 0;               // position in the smem ring
@@ -319,28 +320,27 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         mbar_wait(&full_bar[s], phase);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         tcgen05_fence_after();
-        if (elect_one()) {
-          trace(p, 2, 0, it_global);
-          // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-          if (!a_tma) fence_proxy_async_smem();
-          // descriptor address field is in 16-byte units: + stage / atom offset, + 32 bytes per K=8 step
-          const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
-          const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
-          if (!skip_mma) {
+        trace(p, 2, 0, it_global);
+        // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+        if (!a_tma) fence_proxy_async_smem();
+        // descriptor address field is in 16-byte units: + stage / atom offset, + 32 bytes per K=8 step
+        const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
+        const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
+        if (!skip_mma) {
 #pragma unroll
-            for (int a = 0; a < C::KB; ++a) {
-              if (a >= na) break;
+          for (int a = 0; a < C::KB; ++a) {
+            if (a >= na) break;
 #pragma unroll
-              for (int k = 0; k < BK / 8; ++k)
-                umma_tf32_ss(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
-                             (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
+                           (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
-          if (last) umma_commit(&tmem_full_bar[acc]);            // accumulator complete
-          trace(p, 2, 1, it_global);
         }
+        umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
+        if (last) umma_commit(&tmem_full_bar[acc]);            // accumulator complete
+        trace(p, 2, 1, it_global);
       }
+    }
     }
   } else {
     // ------------------------------------------------------------------ epilogue
