@@ -394,7 +394,7 @@ def run_ours(args, wl):
         """refine -> global scores -> MH chain -> accepted rows (global order)."""
         x = refiner.build_refiner(h0, None, "deterministic")
         sig_local = torch.sigmoid(refiner.optimal_logit)
-        sig = D.gather_scores(sig_local) if world > 1 else sig_local
+        sig = D.gather_scores(sig_local, sizes=[batch] * world) if world > 1 else sig_local
         emit = mh.select(sig)
         if world > 1:
             acc = D.gather_accepted(x, emit.long(), bounds)

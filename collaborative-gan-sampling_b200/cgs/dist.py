@@ -27,15 +27,20 @@ def shard_bounds(n_global, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_scores(local_scores, group=None):
-    """[n_local] -> [n_global] in rank order (equal shard sizes use all_gather_into_tensor, ragged ones pad)."""
+def gather_scores(local_scores, group=None, sizes=None):
+    """[n_local] -> [n_global] in rank order (equal shard sizes use all_gather_into_tensor, ragged ones pad).
+
+    ``sizes`` = per-rank shard sizes when the caller knows them (``shard_bounds``): skips the size exchange and its
+    host synchronisation."""
     rank, ws = world()
     if ws == 1:
         return local_scores
-    n = torch.tensor([local_scores.numel()], dtype=torch.int64, device=local_scores.device)
-    sizes = [torch.zeros_like(n) for _ in range(ws)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n = torch.tensor([local_scores.numel()], dtype=torch.int64, device=local_scores.device)
+        got = torch.empty(ws, dtype=torch.int64, device=local_scores.device)
+        dist.all_gather_into_tensor(got, n, group=group)
+        sizes = got.tolist()
+    sizes = [int(v) for v in sizes]
     m = max(sizes)
     if min(sizes) == m:
         out = torch.empty(ws * m, dtype=local_scores.dtype, device=local_scores.device)
@@ -43,56 +48,64 @@ def gather_scores(local_scores, group=None):
         return out
     pad = torch.zeros(m, dtype=local_scores.dtype, device=local_scores.device)
     pad[:local_scores.numel()] = local_scores
-    bufs = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+    out = torch.empty(ws * m, dtype=local_scores.dtype, device=local_scores.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m:r * m + c] for r, c in enumerate(sizes)])
+
+
+def owned_runs(src_global, bounds):
+    """For an ascending global source-row list and contiguous ascending row blocks ``bounds[r] = (lo, hi)``: the
+    positions [start_r, stop_r) of the rows each rank owns.  One searchsorted, one host read-back."""
+    if src_global.numel() == 0:
+        return [(0, 0) for _ in bounds]
+    edges = torch.tensor([lo for lo, _ in bounds] + [bounds[-1][1]], device=src_global.device, dtype=src_global.dtype)
+    pos = torch.searchsorted(src_global, edges).tolist()
+    return [(pos[r], pos[r + 1]) for r in range(len(bounds))]
 
 
 def owned_slice(src_global, lo, hi):
     """Positions of an ascending global source-row list that fall in [lo, hi) -> (start, stop) of the run."""
-    if src_global.numel() == 0:
-        return 0, 0
-    start = int(torch.searchsorted(src_global, torch.tensor(lo, device=src_global.device, dtype=src_global.dtype)))
-    stop = int(torch.searchsorted(src_global, torch.tensor(hi, device=src_global.device, dtype=src_global.dtype)))
-    return start, stop
+    return owned_runs(src_global, [(lo, hi)])[0]
 
 
 def gather_accepted(local_rows, src_global, bounds, group=None):
     """All-gather(v) of the accepted rows in global order.
 
     ``local_rows`` [n_local, ...] are this rank's samples; ``bounds[r] = (lo, hi)`` are the global row blocks of every
-    rank (``shard_bounds``); ``src_global`` is the ascending list of accepted / emitted GLOBAL row ids, identical on
-    every rank because every rank evaluated the same global chain.  Ownership is a pure function of that list, so
-    all counts are known everywhere without a collective; one padded all_gather moves the rows.
+    rank (``shard_bounds``: contiguous, ascending); ``src_global`` is the ascending list of accepted / emitted GLOBAL
+    row ids, identical on every rank because every rank evaluated the same global chain.  Ownership is a pure function
+    of that list, so all counts are known everywhere without a collective; one padded all_gather moves the rows.
     Returns [len(src_global), ...] on every rank.
     """
     rank, ws = world()
-    lo, hi = bounds[rank]
-    start, stop = owned_slice(src_global, lo, hi)
+    runs = owned_runs(src_global, bounds)
+    lo = bounds[rank][0]
+    start, stop = runs[rank]
     mine = local_rows[(src_global[start:stop] - lo).long()] if stop > start else local_rows[:0]
     if ws == 1:
         return mine
-    counts = []
-    for rlo, rhi in bounds:
-        a, b = owned_slice(src_global, rlo, rhi)
-        counts.append(b - a)
+    counts = [b - a for a, b in runs]
     m = max(counts) if counts else 0
     if m == 0:
         return local_rows[:0]
     pad = torch.zeros((m,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
     pad[:mine.shape[0]] = mine
-    bufs = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)])
+    out = torch.empty((ws * m,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if min(counts) == m:
+        return out
+    return torch.cat([out[r * m:r * m + c] for r, c in enumerate(counts)])
 
 
 def reduce_stats(n_accepted, score_sum, score_max, group=None):
     """(sum, sum, max) all-reduce of the acceptance / score statistics; returns python floats."""
     rank, ws = world()
     dev = score_sum.device if isinstance(score_sum, torch.Tensor) else "cpu"
-    s = torch.tensor([float(n_accepted), float(score_sum)], dtype=torch.float64, device=dev)
-    m = torch.tensor([float(score_max)], dtype=torch.float64, device=dev)
-    if ws > 1:
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-    return float(s[0]), float(s[1]), float(m[0])
+    if ws == 1:
+        return float(n_accepted), float(score_sum), float(score_max)
+    # one exchange: every rank contributes (n, sum, max); sums and the max are formed locally in rank order
+    mine = torch.stack([torch.as_tensor(v, dtype=torch.float64, device=dev).reshape(()) for v in (n_accepted, score_sum, score_max)])
+    allv = torch.empty(ws * 3, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.view(ws, 3).cpu()
+    return float(allv[:, 0].sum()), float(allv[:, 1].sum()), float(allv[:, 2].max())
