@@ -46,7 +46,7 @@ WORKLOADS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
@@ -69,11 +69,18 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None             # wall-clock window of the timed region (mark_start / mark_end)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -82,7 +89,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -94,7 +101,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # samples taken inside the timed window (the sampler starts before the warm-up so it is already running);
+        # a window shorter than the sampling period falls back to every sample taken under load
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.05]
+        in_window = len(rows)
+        if not rows:
+            rows = [r for _, r in self.rows]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -110,7 +123,7 @@ class ClockSampler:
         # median over the upper half = clocks under load (idle samples before/after the region are low)
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": in_window}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -403,14 +416,15 @@ def run_ours(args, wl):
         return x, acc, sig_local
 
     # ---- device-timed region: inputs resident in HBM ------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()                       # running through the warm-up; only samples inside the timed window count
     for _ in range(args.warmup):
         hot_path(h0_dev)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_start()
     launches0 = lib.cgs_launch_count() + refiner.replayed_launches
     step_ms = []
     n_acc = 0
@@ -427,6 +441,7 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    clocks.mark_end()
     launches = (lib.cgs_launch_count() + refiner.replayed_launches - launches0) // max(args.steps, 1)
     clk = clocks.stop() if rank == 0 else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
