@@ -77,20 +77,9 @@ __device__ __forceinline__ float epi_fast(const EdgeEpi& e, float a, float x0, f
   return ROUND ? tf32_rn(o) : o;
 }
 
-template <int MODE, bool ROUND>
-__global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWideParams p, int ksteps, int ntiles, int RO,
-                                                                  int bands, unsigned long long fd_bands,
-                                                                  unsigned long long fd_ow) {
-  extern __shared__ float4 ew_smem4[];
-  const int PR = 2 * RO + p.k - 2;           // staged input rows per band
-  const int patch_px = PR * p.pitch;         // pixels (float4) per patch buffer
-  float2* bfrag = reinterpret_cast<float2*>(ew_smem4);                          // [ksteps][8][32]
-  float4* patch4 = ew_smem4 + ksteps * EW_NT * 32 / 2;                          // [2][PR][pitch]
-  __shared__ int koff_s[EW_KMAX];
-  __shared__ float bias_s[EW_NT * 8];
+// One-time set-up of an edge_wide CTA: k -> patch offset table, bias, weights in mma fragment order.
+__device__ __forceinline__ void wide_setup(const EdgeWideParams& p, int ksteps, float2* bfrag, int* koff_s, float* bias_s) {
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   const int CI = p.cimg;
   const int kreal = p.k * p.k * CI;
   const int prow = p.pitch * 4;              // floats per staged row
@@ -120,6 +109,101 @@ __global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWide
     }
     bfrag[idx] = make_float2(b[0], b[1]);
   }
+}
+
+// The band's GEMM + epilogue: `patch` holds the staged input rows ([rows][pitch][4] floats, row 0 = image row
+// 2*oy0 - pad_y), npx output pixels starting at global pixel m0.  Each warp takes 16 pixels x 64 channels at a time.
+template <int MODE, bool ROUND>
+__device__ __forceinline__ void wide_band(const EdgeWideParams& p, int ksteps, const float* patch, const float2* bfrag,
+                                          const int* koff_s, const float* bias_s, int npx, int m0,
+                                          unsigned long long fd_ow) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int prow = p.pitch * 4;
+  for (int mt = warp; mt * 16 < npx; mt += EW_THREADS / 32) {
+    // the two pixels (rows g, g+8 of the m16 tile) this thread gathers for and stores
+    int base[2], mloc[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ml = mt * 16 + h * 8 + g;
+      const int oyr = fast_div(ml, fd_ow), ox = ml - oyr * p.OW;
+      const bool ok = ml < npx;
+      base[h] = ok ? (2 * oyr * prow + 2 * ox * 4) : 0;
+      mloc[h] = ok ? ml : -1;
+    }
+    float acc[EW_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < EW_NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int o0 = koff_s[ks * 8 + t];
+      const int o1 = koff_s[ks * 8 + t + 4];
+      const uint32_t a0 = __float_as_uint(patch[base[0] + o0]);
+      const uint32_t a1 = __float_as_uint(patch[base[1] + o0]);
+      const uint32_t a2 = __float_as_uint(patch[base[0] + o1]);
+      const uint32_t a3 = __float_as_uint(patch[base[1] + o1]);
+#pragma unroll
+      for (int nt = 0; nt < EW_NT; ++nt) {
+        const float2 bq = bfrag[(ks * EW_NT + nt) * 32 + lane];
+        mma_tf32(acc[nt], a0, a1, a2, a3, __float_as_uint(bq.x), __float_as_uint(bq.y));
+      }
+    }
+    // epilogue: thread owns columns nt*8 + 2t, +1 of its two rows; a quad writes one 32-byte sector
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (mloc[h] < 0) continue;
+      const size_t ro = (size_t)(m0 + mloc[h]) * p.ON + 2 * t;
+      float* orow = p.out + ro;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float2 x0[EW_NT / 2], x1[EW_NT / 2];
+#pragma unroll
+        for (int q = 0; q < EW_NT / 2; ++q) {
+          const int nt = half * (EW_NT / 2) + q;
+          x1[q] = make_float2(0.f, 0.f);
+          if (MODE == EM_FWD_SLOPE) {
+            x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
+          } else if (MODE == EM_BWD_SLOPE) {
+            x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
+          } else {
+            x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
+            if (p.e.epi == EPI_BWD) {
+              x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
+            } else if (p.e.epi == EPI_UPDATE) {
+              x0[q] = *reinterpret_cast<const float2*>(orow + nt * 8);
+              if (!p.e.sgd && !p.e.first) x1[q] = *reinterpret_cast<const float2*>(p.e.mom + ro + nt * 8);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < EW_NT / 2; ++q) {
+          const int nt = half * (EW_NT / 2) + q;
+          float2 m2 = make_float2(0.f, 0.f), o;
+          o.x = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h], x0[q].x, x1[q].x, &m2.x);
+          o.y = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h + 1], x0[q].y, x1[q].y, &m2.y);
+          if (MODE >= EM_UPDATE && p.e.epi == EPI_UPDATE && !p.e.sgd) *reinterpret_cast<float2*>(p.e.mom + ro + nt * 8) = m2;
+          *reinterpret_cast<float2*>(orow + nt * 8) = o;
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, bool ROUND>
+__global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWideParams p, int ksteps, int ntiles, int RO,
+                                                                  int bands, unsigned long long fd_bands,
+                                                                  unsigned long long fd_ow) {
+  extern __shared__ float4 ew_smem4[];
+  const int PR = 2 * RO + p.k - 2;           // staged input rows per band
+  const int patch_px = PR * p.pitch;         // pixels (float4) per patch buffer
+  float2* bfrag = reinterpret_cast<float2*>(ew_smem4);                          // [ksteps][8][32]
+  float4* patch4 = ew_smem4 + ksteps * EW_NT * 32 / 2;                          // [2][PR][pitch]
+  __shared__ int koff_s[EW_KMAX];
+  __shared__ float bias_s[EW_NT * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wide_setup(p, ksteps, bfrag, koff_s, bias_s);
 
   // async copy of the input rows of one tile into patch buffer `buf`
   auto stage_patch = [&](int tile, int buf) {
@@ -150,76 +234,8 @@ __global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWide
     cp_async_commit();
     cp_async_wait<1>();                      // this tile's input rows have landed
     __syncthreads();
-    const float* patch = reinterpret_cast<const float*>(patch4 + cur * patch_px);
-    for (int mt = warp; mt * 16 < npx; mt += EW_THREADS / 32) {
-      // the two pixels (rows g, g+8 of the m16 tile) this thread gathers for and stores
-      int base[2], mloc[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ml = mt * 16 + h * 8 + g;
-        const int oyr = fast_div(ml, fd_ow), ox = ml - oyr * p.OW;
-        const bool ok = ml < npx;
-        base[h] = ok ? (2 * oyr * prow + 2 * ox * 4) : 0;
-        mloc[h] = ok ? ml : -1;
-      }
-      float acc[EW_NT][4];
-#pragma unroll
-      for (int nt = 0; nt < EW_NT; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-#pragma unroll 2
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int o0 = koff_s[ks * 8 + t];
-        const int o1 = koff_s[ks * 8 + t + 4];
-        const uint32_t a0 = __float_as_uint(patch[base[0] + o0]);
-        const uint32_t a1 = __float_as_uint(patch[base[1] + o0]);
-        const uint32_t a2 = __float_as_uint(patch[base[0] + o1]);
-        const uint32_t a3 = __float_as_uint(patch[base[1] + o1]);
-#pragma unroll
-        for (int nt = 0; nt < EW_NT; ++nt) {
-          const float2 bq = bfrag[(ks * EW_NT + nt) * 32 + lane];
-          mma_tf32(acc[nt], a0, a1, a2, a3, __float_as_uint(bq.x), __float_as_uint(bq.y));
-        }
-      }
-      // epilogue: thread owns columns nt*8 + 2t, +1 of its two rows; a quad writes one 32-byte sector
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (mloc[h] < 0) continue;
-        const size_t ro = (size_t)(m0 + mloc[h]) * p.ON + 2 * t;
-        float* orow = p.out + ro;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float2 x0[EW_NT / 2], x1[EW_NT / 2];
-#pragma unroll
-          for (int q = 0; q < EW_NT / 2; ++q) {
-            const int nt = half * (EW_NT / 2) + q;
-            x1[q] = make_float2(0.f, 0.f);
-            if (MODE == EM_FWD_SLOPE) {
-              x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
-            } else if (MODE == EM_BWD_SLOPE) {
-              x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
-            } else {
-              x0[q] = *reinterpret_cast<const float2*>(bias_s + nt * 8 + 2 * t);
-              if (p.e.epi == EPI_BWD) {
-                x0[q] = __ldg(reinterpret_cast<const float2*>(p.e.aux + ro + nt * 8));
-              } else if (p.e.epi == EPI_UPDATE) {
-                x0[q] = *reinterpret_cast<const float2*>(orow + nt * 8);
-                if (!p.e.sgd && !p.e.first) x1[q] = *reinterpret_cast<const float2*>(p.e.mom + ro + nt * 8);
-              }
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < EW_NT / 2; ++q) {
-            const int nt = half * (EW_NT / 2) + q;
-            float2 m2 = make_float2(0.f, 0.f), o;
-            o.x = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h], x0[q].x, x1[q].x, &m2.x);
-            o.y = epi_fast<MODE, ROUND>(p.e, acc[nt][2 * h + 1], x0[q].y, x1[q].y, &m2.y);
-            if (MODE >= EM_UPDATE && p.e.epi == EPI_UPDATE && !p.e.sgd) *reinterpret_cast<float2*>(p.e.mom + ro + nt * 8) = m2;
-            *reinterpret_cast<float2*>(orow + nt * 8) = o;
-          }
-        }
-      }
-    }
+    wide_band<MODE, ROUND>(p, ksteps, reinterpret_cast<const float*>(patch4 + cur * patch_px), bfrag, koff_s, bias_s, npx,
+                           m0, fd_ow);
     __syncthreads();                         // patch[cur] may be overwritten from here on
   }
   cp_async_wait<0>();
@@ -235,17 +251,11 @@ constexpr int EN_THREADS = 256;
 constexpr int EN_ROWS = 256;        // col rows (input pixels incl. halo) per tile
 constexpr int EN_KSTEPS = 8;        // K = 64
 
+// Weights of an edge_narrow pass in mma fragment order: [8 k-steps][NT][32 lanes] float2.
 template <int NT, int CI>
-__global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarrowParams p, int ntiles) {
-  constexpr int CP = NT * 8 + 4;    // col row pitch (floats)
-  extern __shared__ float2 en_smem[];
-  float2* bfrag = en_smem;                                              // [8][NT][32]
-  float* col_s = reinterpret_cast<float*>(en_smem + EN_KSTEPS * NT * 32);   // [EN_ROWS][CP]
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void narrow_setup(const EdgeNarrowParams& p, float2* bfrag) {
   const int nreal = p.k * p.k * CI;
-  for (int idx = tid; idx < EN_KSTEPS * NT * 32; idx += EN_THREADS) {
+  for (int idx = threadIdx.x; idx < EN_KSTEPS * NT * 32; idx += EN_THREADS) {
     const int l = idx & 31, nt = (idx >> 5) % NT, ks = idx / (NT * 32);
     const int n = nt * 8 + (l >> 2);
     // logical k slots (t, t+4) of k-step ks are input channels 16*(ks/2) + 4t + 2*(ks%2) + {0, 1}
@@ -257,6 +267,103 @@ __global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarro
     }
     bfrag[idx] = b;
   }
+}
+
+// col[pixel][(ky,kx,c)] = in[pixel][:] . W for the mt_rows input pixels starting at src; result in shared memory.
+template <int NT>
+__device__ __forceinline__ void narrow_mma(const float* src, int K, int mt_rows, const float2* bfrag, float* col_s) {
+  constexpr int CP = NT * 8 + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nmt = (mt_rows + 15) >> 4;
+  for (int mt = warp; mt < nmt; mt += EN_THREADS / 32) {
+    const int ra = mt * 16 + g, rb = ra + 8;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      va[j] = ra < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)ra * K + 16 * j + 4 * t))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[j] = rb < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)rb * K + 16 * j + 4 * t))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float2 be = bfrag[((2 * j) * NT + nt) * 32 + lane];
+        mma_tf32(acc[nt], __float_as_uint(va[j].x), __float_as_uint(vb[j].x), __float_as_uint(va[j].y),
+                 __float_as_uint(vb[j].y), __float_as_uint(be.x), __float_as_uint(be.y));
+        const float2 bo = bfrag[((2 * j + 1) * NT + nt) * 32 + lane];
+        mma_tf32(acc[nt], __float_as_uint(va[j].z), __float_as_uint(vb[j].z), __float_as_uint(va[j].w),
+                 __float_as_uint(vb[j].w), __float_as_uint(bo.x), __float_as_uint(bo.y));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      *reinterpret_cast<float2*>(col_s + ra * CP + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(col_s + rb * CP + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
+// col2im + epilogue over output rows [y_lo, y_hi) of image b (margins of the pitched layout are written as zeros): one
+// warp per output row, so the ky taps are warp-uniform; only taps of the right parity are visited, in a fixed order.
+// The result goes to global memory (unless `out` is null) and, if `patch` is given, into a shared-memory copy of the
+// pitched image whose row 0 is image row -patch_row0 (the consumer's staged input, fused pair kernels).
+template <int NT, int CI>
+__device__ __forceinline__ void narrow_col2im(const EdgeNarrowParams& p, const float* col_s, int b, int iy_lo, int rows_in,
+                                              int y_lo, int y_hi, float* out, float4* patch, int patch_row0) {
+  constexpr int CP = NT * 8 + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 bias4 = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float4*>(p.e.bias))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int y = y_lo + warp; y < y_hi; y += EN_THREADS / 32) {
+    const int ky0 = (y + p.pad_y) & 1;
+    const size_t grow = ((size_t)b * p.OH + y) * p.out_pitch * 4;
+    for (int xc = lane; xc < p.out_pitch; xc += 32) {
+      const int x = xc - p.out_xoff;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (x >= 0 && x < p.OW) {
+        float a[CI];
+#pragma unroll
+        for (int c = 0; c < CI; ++c) a[c] = 0.f;
+        const int kx0 = (x + p.pad_x) & 1;
+        for (int ky = ky0; ky < p.k; ky += 2) {
+          const int lr = ((y + p.pad_y - ky) >> 1) - iy_lo;      // negative (above the image / tile) -> skipped
+          if ((unsigned)lr >= (unsigned)rows_in) continue;
+          for (int kx = kx0; kx < p.k; kx += 2) {
+            const int ix = (x + p.pad_x - kx) >> 1;
+            if ((unsigned)ix >= (unsigned)p.IW) continue;
+            const float* cp = col_s + (lr * p.IW + ix) * CP + (ky * p.k + kx) * CI;
+#pragma unroll
+            for (int c = 0; c < CI; ++c) a[c] += cp[c];
+          }
+        }
+        float4 x0 = bias4;
+        if (p.e.epi == EPI_BWD) x0 = __ldg(reinterpret_cast<const float4*>(p.e.aux + grow + xc * 4));
+        const float xs[3] = {x0.x, x0.y, x0.z};
+        float unused;
+#pragma unroll
+        for (int c = 0; c < CI; ++c) o[c] = epilogue1(p.e, a[c], xs[c], 0.f, &unused);
+      }
+      const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+      if (out) *reinterpret_cast<float4*>(out + grow + xc * 4) = v;
+      if (patch) patch[(y + patch_row0) * p.out_pitch + xc] = v;
+    }
+  }
+}
+
+template <int NT, int CI>
+__global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarrowParams p, int ntiles) {
+  extern __shared__ float2 en_smem[];
+  float2* bfrag = en_smem;                                              // [8][NT][32]
+  float* col_s = reinterpret_cast<float*>(en_smem + EN_KSTEPS * NT * 32);   // [EN_ROWS][CP]
+  narrow_setup<NT, CI>(p, bfrag);
   __syncthreads();
   pdl_launch_dependents();
   pdl_wait();                                // weights above are constants; activations from here on
@@ -266,82 +373,51 @@ __global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarro
     const int r0 = (tile - b * p.bands) * p.R;
     const int iy_lo = max(0, r0 - p.halo_lo);
     const int iy_hi = min(p.IH, r0 + p.R + p.halo_hi);
-    const int mt_rows = (iy_hi - iy_lo) * p.IW;
-    const float* src = p.in + ((size_t)b * p.IH + iy_lo) * p.IW * p.K;
-    const int nmt = (mt_rows + 15) >> 4;
-    for (int mt = warp; mt < nmt; mt += EN_THREADS / 32) {
-      const int ra = mt * 16 + g, rb = ra + 8;
-      float4 va[4], vb[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        va[j] = ra < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)ra * p.K + 16 * j + 4 * t))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[j] = rb < mt_rows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)rb * p.K + 16 * j + 4 * t))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float acc[NT][4];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float2 be = bfrag[((2 * j) * NT + nt) * 32 + lane];
-          mma_tf32(acc[nt], __float_as_uint(va[j].x), __float_as_uint(vb[j].x), __float_as_uint(va[j].y),
-                   __float_as_uint(vb[j].y), __float_as_uint(be.x), __float_as_uint(be.y));
-          const float2 bo = bfrag[((2 * j + 1) * NT + nt) * 32 + lane];
-          mma_tf32(acc[nt], __float_as_uint(va[j].z), __float_as_uint(vb[j].z), __float_as_uint(va[j].w),
-                   __float_as_uint(vb[j].w), __float_as_uint(bo.x), __float_as_uint(bo.y));
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        *reinterpret_cast<float2*>(col_s + ra * CP + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<float2*>(col_s + rb * CP + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
-      }
-    }
+    narrow_mma<NT>(p.in + ((size_t)b * p.IH + iy_lo) * p.IW * p.K, p.K, (iy_hi - iy_lo) * p.IW, bfrag, col_s);
     __syncthreads();
-    // col2im + epilogue over the band's output rows (margins of the pitched layout are written as zeros): one warp
-    // per output row, so the ky taps are warp-uniform; only taps of the right parity are visited
-    const int y_lo = 2 * r0;
-    const int y_hi = min(p.OH, 2 * (r0 + p.R));
-    const int rows_in = iy_hi - iy_lo;
-    const float4 bias4 = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float4*>(p.e.bias))
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int y = y_lo + warp; y < y_hi; y += EN_THREADS / 32) {
-      const int ky0 = (y + p.pad_y) & 1;
-      float* orow = p.out + ((size_t)b * p.OH + y) * p.out_pitch * 4;
-      for (int xc = lane; xc < p.out_pitch; xc += 32) {
-        const int x = xc - p.out_xoff;
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        if (x >= 0 && x < p.OW) {
-          float a[CI];
-#pragma unroll
-          for (int c = 0; c < CI; ++c) a[c] = 0.f;
-          const int kx0 = (x + p.pad_x) & 1;
-          for (int ky = ky0; ky < p.k; ky += 2) {
-            const int lr = ((y + p.pad_y - ky) >> 1) - iy_lo;      // negative (above the image / tile) -> skipped
-            if ((unsigned)lr >= (unsigned)rows_in) continue;
-            for (int kx = kx0; kx < p.k; kx += 2) {
-              const int ix = (x + p.pad_x - kx) >> 1;
-              if ((unsigned)ix >= (unsigned)p.IW) continue;
-              const float* cp = col_s + (lr * p.IW + ix) * CP + (ky * p.k + kx) * CI;
-#pragma unroll
-              for (int c = 0; c < CI; ++c) a[c] += cp[c];
-            }
-          }
-          float4 x0 = bias4;
-          if (p.e.epi == EPI_BWD) x0 = __ldg(reinterpret_cast<const float4*>(p.e.aux + ((size_t)b * p.OH + y) * p.out_pitch * 4 + xc * 4));
-          const float xs[3] = {x0.x, x0.y, x0.z};
-          float unused;
-#pragma unroll
-          for (int c = 0; c < CI; ++c) o[c] = epilogue1(p.e, a[c], xs[c], 0.f, &unused);
-        }
-        *reinterpret_cast<float4*>(orow + xc * 4) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    }
+    narrow_col2im<NT, CI>(p, col_s, b, iy_lo, iy_hi - iy_lo, 2 * r0, min(p.OH, 2 * (r0 + p.R)), p.out, nullptr, 0);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge_pair: the narrow pass of one layer followed by the wide pass of the next on the same image, in one kernel:
+// forward   G's last deconv (-> image, tanh) + D's first conv (-> 64 channels, LeakyReLU)
+// backward  D's first conv data-gradient (x tanh') + G's last deconv data-gradient (x ReLU' / policy step)
+// The image (or its gradient) goes from the col2im of the first pass straight into the staged-input buffer of the
+// second; the forward image is also written to global memory (best-of-K keep, derivative operand), its gradient is
+// not.  One image per tile: used when a whole image fits one tile of both passes (MNIST-sized nets).
+// ---------------------------------------------------------------------------------------------
+template <int NT, int CI, int MODE, bool ROUND>
+__global__ void __launch_bounds__(EN_THREADS, 4) edge_pair_kernel(const EdgeNarrowParams pn, const EdgeWideParams pw,
+                                                                  int ksteps_w, int store_image,
+                                                                  unsigned long long fd_ow) {
+  static_assert(EN_THREADS == EW_THREADS, "both passes use the same CTA shape");
+  extern __shared__ float4 ep_smem4[];
+  const int PR = 2 * pw.OH + pw.k - 2;                                   // staged rows of the wide pass (whole image)
+  float2* bfrag_n = reinterpret_cast<float2*>(ep_smem4);                 // [8][NT][32]
+  float2* bfrag_w = bfrag_n + EN_KSTEPS * NT * 32;                       // [ksteps_w][8][32]
+  float4* patch4 = reinterpret_cast<float4*>(bfrag_w + ksteps_w * EW_NT * 32);   // [PR][pitch]
+  float* col_s = reinterpret_cast<float*>(patch4 + PR * pw.pitch);       // [IH*IW rounded to 16][CP]
+  __shared__ int koff_s[EW_KMAX];
+  __shared__ float bias_s[EW_NT * 8];
+  narrow_setup<NT, CI>(pn, bfrag_n);
+  wide_setup(pw, ksteps_w, bfrag_w, koff_s, bias_s);
+  // rows of the staged image outside the image stay zero for the whole kernel
+  for (int idx = threadIdx.x; idx < PR * pw.pitch; idx += EN_THREADS) {
+    const int iy = idx / pw.pitch - pw.pad_y;
+    if ((unsigned)iy >= (unsigned)pw.IH) patch4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  const int npx = pw.OH * pw.OW;
+  for (int b = blockIdx.x; b < pn.B; b += gridDim.x) {
+    narrow_mma<NT>(pn.in + (size_t)b * pn.IH * pn.IW * pn.K, pn.K, pn.IH * pn.IW, bfrag_n, col_s);
+    __syncthreads();
+    narrow_col2im<NT, CI>(pn, col_s, b, 0, pn.IH, 0, pn.OH, store_image ? pn.out : nullptr, patch4, pw.pad_y);
+    __syncthreads();
+    wide_band<MODE, ROUND>(pw, ksteps_w, reinterpret_cast<const float*>(patch4), bfrag_w, koff_s, bias_s, npx, b * npx, fd_ow);
     __syncthreads();
   }
 }
@@ -432,8 +508,8 @@ int launch_edge_wide(const EdgeWideParams& p, cudaStream_t st) {
   return launch_wide_mode<EM_GENERIC, false>(p, B, st);
 }
 
-int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
-  if (p.B <= 0) return CGS_OK;
+namespace {
+int narrow_geometry(EdgeNarrowParams& p) {
   // rows of the input needed above / below a band of R input rows (its 2R output rows gather taps
   // iy = (y + pad_y - ky) / 2): brute force over a sample band, the answer does not depend on R or r0
   int lo = 0, hi = 0;
@@ -458,6 +534,71 @@ int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
     if (p.R < 1) return set_error(CGS_ERR_UNSUPPORTED, "edge_narrow: image row too wide for the tile");
   }
   p.bands = (p.IH + p.R - 1) / p.R;
+  return CGS_OK;
+}
+
+template <int NT, int CI, int MODE, bool ROUND>
+int launch_pair_inst(const EdgeNarrowParams& pn, const EdgeWideParams& pw, int store_image, cudaStream_t st) {
+  constexpr int CP = NT * 8 + 4;
+  const int ksteps_w = (pw.k * pw.k * pw.cimg + 7) / 8;
+  const int PR = 2 * pw.OH + pw.k - 2;
+  const int col_rows = ((pn.IH * pn.IW + 15) / 16) * 16;
+  const size_t smem = (size_t)EN_KSTEPS * NT * 32 * sizeof(float2) + (size_t)ksteps_w * EW_NT * 32 * sizeof(float2) +
+                      (size_t)PR * pw.pitch * sizeof(float4) + (size_t)col_rows * CP * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(edge_pair_kernel<NT, CI, MODE, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_pair): %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_pair_kernel<NT, CI, MODE, ROUND>, EN_THREADS, smem);
+  if (e != cudaSuccess || per_sm < 1) return set_error(CGS_ERR_CUDA, "edge_pair occupancy query failed");
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > pn.B) grid = pn.B;
+  e = launch_pdl(edge_pair_kernel<NT, CI, MODE, ROUND>, dim3((unsigned)grid), dim3(EN_THREADS), smem, st, pn, pw, ksteps_w,
+                 store_image, fast_div_magic((unsigned)pw.OW));
+  count_launch();
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_pair_kernel: %s", cudaGetErrorString(e));
+  return check_launch("edge_pair_kernel");
+}
+
+template <int NT, int CI>
+int launch_pair_mode(const EdgeNarrowParams& pn, const EdgeWideParams& pw, int store_image, cudaStream_t st) {
+  const bool rnd = pw.e.round_out != 0;
+  if (pw.e.epi == EPI_FWD && !pw.e.act_tanh)
+    return rnd ? launch_pair_inst<NT, CI, EM_FWD_SLOPE, true>(pn, pw, store_image, st)
+               : launch_pair_inst<NT, CI, EM_FWD_SLOPE, false>(pn, pw, store_image, st);
+  if (pw.e.epi == EPI_BWD && !pw.e.act_tanh)
+    return rnd ? launch_pair_inst<NT, CI, EM_BWD_SLOPE, true>(pn, pw, store_image, st)
+               : launch_pair_inst<NT, CI, EM_BWD_SLOPE, false>(pn, pw, store_image, st);
+  if (pw.e.epi == EPI_UPDATE) return launch_pair_inst<NT, CI, EM_UPDATE, false>(pn, pw, store_image, st);
+  return launch_pair_inst<NT, CI, EM_GENERIC, false>(pn, pw, store_image, st);
+}
+}  // namespace
+
+// One image per tile in both passes, single-channel image, same pitched layout on both sides; the shared-memory
+// footprint (column buffer + staged image + two weight tiles) must leave room for three CTAs per SM.
+bool edge_pair_supported(const EdgeNarrowParams& pn, const EdgeWideParams& pw) {
+  if (!edge_narrow_supported(pn.K, pn.k, pn.cimg, pn.IW) || !edge_wide_supported(pw.N, pw.k, pw.cimg)) return false;
+  if (pn.cimg != 1 || pw.cimg != 1) return false;
+  if (pn.IH * pn.IW > EN_ROWS || pw.OH * pw.OW > EW_TILE_PX) return false;
+  if (pn.OH != pw.IH || pn.out_pitch != pw.pitch || pn.out_xoff != pw.xoff || pw.ON != pw.N) return false;
+  return true;
+}
+
+int launch_edge_pair(EdgeNarrowParams pn, const EdgeWideParams& pw, int store_image, cudaStream_t st) {
+  if (pn.B <= 0) return CGS_OK;
+  if ((long long)pn.B * pw.OH * pw.OW * pw.ON >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large for 32-bit indexing; split the batch");
+  if (int rc = narrow_geometry(pn)) return rc;
+  if (pn.k == 4) return launch_pair_mode<2, 1>(pn, pw, store_image, st);
+  if (pn.k == 5) return launch_pair_mode<4, 1>(pn, pw, store_image, st);
+  return set_error(CGS_ERR_UNSUPPORTED, "edge_pair: unsupported kernel size");
+}
+
+int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
+  if (p.B <= 0) return CGS_OK;
+  if (int rc = narrow_geometry(p)) return rc;
   if (p.k == 4 && p.cimg == 1) return launch_narrow_nt<2, 1>(p, st);
   if (p.k == 5 && p.cimg == 1) return launch_narrow_nt<4, 1>(p, st);
   if (p.k == 4 && p.cimg == 3) return launch_narrow_nt<6, 3>(p, st);

@@ -480,6 +480,65 @@ int launch_splitk_reduce(ConvGemmParams pe, const float* part, int S, int64_t B,
   return check_launch("splitk_reduce_kernel");
 }
 
+// Parameters of the fused image-edge kernels (edge_conv.cuh) for a scatter- / window-lowered pass; false when the
+// shape is not covered (the general tcgen05 lowering runs instead) or the kernels are switched off.
+bool make_edge_narrow(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
+                      bool dense_image, int w_cols, EdgeNarrowParams& q) {
+  const LayerShape s = layer_shape(L);
+  const int kch = backward ? L.cout : L.cin, cimg = backward ? L.cin : L.cout;
+  const int iw = backward ? s.wout : L.win;
+  if (!edge_kernels_enabled() || !use_scatter(L, backward) || !edge_narrow_supported(kch, L.k, cimg, iw) || w_cols != kch)
+    return false;
+  std::memset(&q, 0, sizeof(q));
+  q.in = in; q.out = out; q.w = backward ? L.w_bwd : L.w_fwd;
+  q.B = (int)B; q.K = kch; q.k = L.k; q.cimg = cimg;
+  if (!backward) {
+    q.IH = L.hin; q.IW = L.win; q.OH = s.hout; q.OW = s.wout;
+    q.pad_y = same_pad_before(s.hout, L.k); q.pad_x = same_pad_before(s.wout, L.k);
+  } else {
+    q.IH = s.hout; q.IW = s.wout; q.OH = L.hin; q.OW = L.win;
+    q.pad_y = same_pad_before(L.hin, L.k); q.pad_x = same_pad_before(L.win, L.k);
+  }
+  q.out_pitch = dense_image ? q.OW : img_pitch(q.OW);
+  q.out_xoff = dense_image ? 0 : IMG_XOFF;
+  q.e = make_edge_epi(e, L.bias);
+  return true;
+}
+
+bool make_edge_wide(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
+                    const ConvGemmParams& wp, EdgeWideParams& q) {     // wp = make_window_params of the same pass
+  const int cimg = backward ? L.cout : L.cin;
+  if (!edge_kernels_enabled() || !edge_wide_supported(wp.N, L.k, cimg) || wp.ON != wp.N) return false;
+  std::memset(&q, 0, sizeof(q));
+  q.in = in; q.out = out; q.w = backward ? L.w_bwd : L.w_fwd;
+  q.IH = wp.IH; q.pitch = wp.in_pitch_px; q.xoff = IMG_XOFF; q.OH = wp.OH; q.OW = wp.OW; q.ON = wp.ON; q.N = wp.N;
+  q.k = L.k; q.cimg = cimg;
+  q.pad_y = same_pad_before(wp.IH, L.k); q.pad_x = same_pad_before(wp.IW, L.k);
+  q.M = (long long)B * wp.OH * wp.OW;
+  q.e = make_edge_epi(e, backward ? nullptr : L.bias);
+  return true;
+}
+
+// The narrow pass of layer `ln` followed by the wide pass of layer `lw` on its output (forward: G's last deconv + D's
+// first conv; backward: their data-gradients in the opposite order) as ONE kernel when both fit a one-image tile.
+// Returns 1 when the pair was launched, 0 when the caller should run the two passes separately, < 0 on error.
+int try_edge_pair(const cgs_layer_desc& ln, const cgs_layer_desc& lw, bool backward, int64_t B, const float* in,
+                  float* mid, float* out, const PassEpi& en, const PassEpi& ew, int store_mid, int math, cudaStream_t st) {
+  if (math != CGS_MATH_TF32_TENSOR || (debug_flags() & 65536) || en.upd) return 0;
+  if (!use_scatter(ln, backward) || !use_window(lw, backward)) return 0;
+  EdgeNarrowParams qn;
+  if (!make_edge_narrow(ln, backward, B, in, mid, en, false, backward ? ln.kcols_bwd : ln.kcols_fwd, qn)) return 0;
+  ConvGemmParams wp;
+  if (make_window_params(lw, backward, B, mid, out, wp) != CGS_OK) return 0;
+  if ((backward ? lw.rows_bwd : lw.rows_fwd) != (backward ? lw.cin : lw.cout) ||
+      (backward ? lw.kcols_bwd : lw.kcols_fwd) != window_kcols(lw)) return 0;
+  EdgeWideParams qw;
+  if (!make_edge_wide(lw, backward, B, mid, out, ew, wp, qw)) return 0;
+  if (!edge_pair_supported(qn, qw)) return 0;
+  if (int rc = launch_edge_pair(qn, qw, store_mid, st)) return rc;
+  return 1;
+}
+
 // One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
 int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
              float* col, int math, cudaStream_t st, bool dense_image = false) {
@@ -491,27 +550,9 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     if (!col) return set_error(CGS_ERR_WORKSPACE, "scatter pass needs a column workspace");
     if (rows != scatter_cols(L)) return set_error(CGS_ERR_INVALID, "weights of this pass must be in scatter layout (%d rows)", scatter_cols(L));
     {
-      const LayerShape s = layer_shape(L);
-      const int kch = backward ? L.cout : L.cin, cimg = backward ? L.cin : L.cout;
-      const int iw = backward ? s.wout : L.win;
-      if (math == CGS_MATH_TF32_TENSOR && edge_kernels_enabled() && !e.upd && edge_narrow_supported(kch, L.k, cimg, iw) &&
-          cols == kch) {
-        EdgeNarrowParams q;
-        std::memset(&q, 0, sizeof(q));
-        q.in = in; q.out = out; q.w = w;
-        q.B = (int)B; q.K = kch; q.k = L.k; q.cimg = cimg;
-        if (!backward) {
-          q.IH = L.hin; q.IW = L.win; q.OH = s.hout; q.OW = s.wout;
-          q.pad_y = same_pad_before(s.hout, L.k); q.pad_x = same_pad_before(s.wout, L.k);
-        } else {
-          q.IH = s.hout; q.IW = s.wout; q.OH = L.hin; q.OW = L.win;
-          q.pad_y = same_pad_before(L.hin, L.k); q.pad_x = same_pad_before(L.win, L.k);
-        }
-        q.out_pitch = dense_image ? q.OW : img_pitch(q.OW);
-        q.out_xoff = dense_image ? 0 : IMG_XOFF;
-        q.e = make_edge_epi(e, L.bias);
+      EdgeNarrowParams q;
+      if (math == CGS_MATH_TF32_TENSOR && !e.upd && make_edge_narrow(L, backward, B, in, out, e, dense_image, cols, q))
         return launch_edge_narrow(q, st);
-      }
     }
     ConvGemmParams p;
     if (int rc = make_scatter_gemm_params(L, backward, B, in, col, p)) return rc;
@@ -579,18 +620,8 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     if (rows != (backward ? L.cin : L.cout) || cols != window_kcols(L))
       return set_error(CGS_ERR_INVALID, "weights of this pass must be in window layout (%d columns)", window_kcols(L));
     if (int rc = make_window_params(L, backward, B, in, out, p)) return rc;
-    const int cimg = backward ? L.cout : L.cin;
-    if (math == CGS_MATH_TF32_TENSOR && edge_kernels_enabled() && edge_wide_supported(p.N, L.k, cimg) && p.ON == p.N) {
-      EdgeWideParams q;
-      std::memset(&q, 0, sizeof(q));
-      q.in = in; q.out = out; q.w = w;
-      q.IH = p.IH; q.pitch = p.in_pitch_px; q.xoff = IMG_XOFF; q.OH = p.OH; q.OW = p.OW; q.ON = p.ON; q.N = p.N;
-      q.k = L.k; q.cimg = cimg;
-      q.pad_y = same_pad_before(p.IH, L.k); q.pad_x = same_pad_before(p.IW, L.k);
-      q.M = (long long)B * p.OH * p.OW;
-      q.e = make_edge_epi(e, backward ? nullptr : L.bias);
-      return launch_edge_wide(q, st);
-    }
+    EdgeWideParams q;
+    if (math == CGS_MATH_TF32_TENSOR && make_edge_wide(L, backward, B, in, out, e, p, q)) return launch_edge_wide(q, st);
   } else if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) {
     return rc;
   }
@@ -853,6 +884,16 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
     // TF32 path: activations that feed another MMA are rounded to TF32 (RN) where they are produced, so the
     // tensor core's operand truncation is exact; the image (returned to the caller) and the head input stay FP32
     e.round_out = (math == CGS_MATH_TF32_TENSOR) && (i != c.n_gtail - 1) && (i != c.n - 1);
+    if (i == c.n_gtail - 1 && i + 1 < c.n) {
+      // generator's last deconv + discriminator's first conv on the same image: one kernel when the shapes allow
+      PassEpi e2;
+      e2.epi = EPI_FWD;
+      e2.act = c.layers[i + 1].act;
+      e2.round_out = (math == CGS_MATH_TF32_TENSOR) && (i + 1 != c.n - 1);
+      const int rc = try_edge_pair(c.layers[i], c.layers[i + 1], false, B, w.act[i], w.act[i + 1], w.act[i + 2], e, e2, 1, math, st);
+      if (rc < 0) return rc;
+      if (rc == 1) { ++i; continue; }
+    }
     if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st)) return rc;
   }
   return CGS_OK;
@@ -873,6 +914,23 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
       e.round_out = (math == CGS_MATH_TF32_TENSOR);
     } else {
       e.upd = upd;
+    }
+    if (i == c.n_gtail && i >= 1) {
+      // data-gradients of D's first conv and G's last deconv: one kernel, the image gradient never leaves the SM
+      PassEpi e2;
+      float* dst2 = (i - 1 == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
+      if (i - 1 > 0) {
+        e2.epi = EPI_BWD;
+        e2.aux = w.act[i - 1];
+        e2.act = c.layers[i - 2].act;
+        e2.round_out = (math == CGS_MATH_TF32_TENSOR);
+      } else {
+        e2.upd = upd;
+      }
+      // the intermediate (image gradient) buffer is only described, never written: any valid pointer of that size
+      const int rc = try_edge_pair(c.layers[i], c.layers[i - 1], true, B, w.g[cur], w.g[cur ^ 1], dst2, e, e2, 0, math, st);
+      if (rc < 0) return rc;
+      if (rc == 1) { --i; cur ^= 1; continue; }
     }
     if (int rc = run_pass(c.layers[i], true, B, w.g[cur], dst, e, w.col, math, st)) return rc;
     cur ^= 1;

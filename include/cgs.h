@@ -242,7 +242,8 @@ CGS_API int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, con
 CGS_API int cgs_debug_trace(unsigned long long* out_host, int capacity);
 /* Developer aid: replace the CGS_DEBUG knobs at run time; returns the previous value.  Bit 4096 routes the image-edge
  * passes (first D conv / last G deconv and their data-gradients) through the general tcgen05 lowerings instead of
- * the fused streaming kernels of csrc/edge_conv.cu. */
+ * the fused streaming kernels of csrc/edge_conv.cu; 65536 runs the edge passes as separate kernels instead of the
+ * paired ones; 16384 disables split-K on the long fc forward; 32768 adds programmatic dependent launch. */
 CGS_API int cgs_debug_set_flags(int flags);
 
 #ifdef __cplusplus

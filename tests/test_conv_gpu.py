@@ -194,8 +194,9 @@ def test_cuda_graph_replay_is_bit_identical(cgs_lib, cuda_device):
 
 def test_launch_and_lowering_knobs_do_not_change_results(cgs_lib, cuda_device):
     """Programmatic dependent launch (bit 32768) reorders nothing: bit-identical.  The fc split-K lowering (off with
-    bit 16384) and the fused edge kernels (off with bit 4096) only change summation order: same refined batch within
-    the TF32 tolerance and the same best step for nearly every sample."""
+    bit 16384), the fused edge kernels (off with bit 4096) and their pairing into one kernel (off with bit 65536) only
+    change summation order or nothing at all: same refined batch within the TF32 tolerance and the same best step for
+    nearly every sample."""
     from cgs import nets as N
     from sampling.collaborator import Refiner
     arch, w, spec = _make("mnist", 5, 3.0, cuda_device, "tf32")
@@ -215,7 +216,7 @@ def test_launch_and_lowering_knobs_do_not_change_results(cgs_lib, cuda_device):
     base = run(0)
     pdl = run(32768)
     assert all(torch.equal(a, b) for a, b in zip(base, pdl))
-    for flags in (16384, 4096, 16384 | 4096):
+    for flags in (16384, 4096, 65536, 16384 | 4096):         # 65536: the two edge pairs as four separate kernels
         x, logit, step = run(flags)
         assert rel_l2(x.cpu().numpy(), base[0].cpu().numpy()) <= 1e-2
         assert float((logit - base[1]).abs().max()) <= 1.5e-2
