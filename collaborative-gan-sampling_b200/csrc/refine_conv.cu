@@ -314,6 +314,11 @@ inline int fc_split(const cgs_layer_desc& L, bool backward) {
   return (L.type == CGS_LAYER_FC && !backward && L.cin >= 4096 && L.cin % (32 * S) == 0) ? S : 1;
 }
 
+inline bool use_fc_split(const cgs_layer_desc& L, bool backward, int64_t B, int math, const float* scratch) {
+  return fc_split(L, backward) > 1 && math == CGS_MATH_TF32_TENSOR && scratch && !(debug_flags() & 16384) &&
+         ((B + 127) / 128) * ((L.cout + 255) / 256) * fc_split(L, backward) <= 2 * 148;
+}
+
 size_t scatter_col_elems(const cgs_layer_desc& L, bool backward) {     // per-sample elements of the pass scratch buffer
   if (fc_split(L, backward) > 1) return (size_t)fc_split(L, backward) * cstride(L.cout);
   if (!use_scatter(L, backward)) return 0;
@@ -541,7 +546,7 @@ int try_edge_pair(const cgs_layer_desc& ln, const cgs_layer_desc& lw, bool backw
 
 // One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
 int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
-             float* col, int math, cudaStream_t st, bool dense_image = false) {
+             float* col, int math, cudaStream_t st, bool dense_image = false, bool defer_reduce = false) {
   const float* w = backward ? L.w_bwd : L.w_fwd;
   const int rows = backward ? L.rows_bwd : L.rows_fwd;
   const int cols = backward ? L.kcols_bwd : L.kcols_fwd;
@@ -584,8 +589,7 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     return check_launch("col2im_kernel");
   }
   ConvGemmParams p;
-  if (const int S = fc_split(L, backward); S > 1 && math == CGS_MATH_TF32_TENSOR && col && !(debug_flags() & 16384) &&
-                                           ((B + 127) / 128) * ((L.cout + 255) / 256) * S <= 2 * 148) {
+  if (const int S = fc_split(L, backward); use_fc_split(L, backward, B, math, col)) {
     if (int rc = make_forward_params(L, B, in, col, p)) return rc;
     ConvGemmParams pe = p;                    // epilogue description of the real output
     pe.out = out;
@@ -614,6 +618,7 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     p.OH = S;
     { static const int bn = env_int("CGS_FC_BN", 256); p.force_bn = bn; }
     if (int rc = launch_gemm(p, w, rows, cols, math, st)) return rc;
+    if (defer_reduce) return CGS_OK;          // the head kernel adds the partial sums itself (head_takes_partials)
     return launch_splitk_reduce(pe, col, S, B, st);
   }
   if (use_window(L, backward)) {
@@ -672,7 +677,30 @@ struct HeadParams {
   float* final_feature; // [B_orig, feat_elems]: state of a sample at the step it exits (early-exit) or nullptr
   float exit_logit;
   int round_out;        // round dpre to TF32 (RN): it feeds a kind::tf32 MMA
+  // split-K producer (fc_split): feat is not materialised; feat[b][k] = act(sum_s part[b][s][k] + fc_bias[k])
+  const float* part;    // [B][S][K] partial sums or nullptr
+  int S;
+  const float* fc_bias;
+  float fc_slope;       // relu 0, lrelu 0.2, none 1 (same expression as the GEMM epilogue: bit-identical)
+  int fc_tanh;
 };
+
+// Input of the head for elements k..k+3 of sample b: the stored activation, or the split-K partial sums added in
+// a fixed order with the fc layer's bias and activation applied (what splitk_reduce_kernel would have stored).
+__device__ __forceinline__ float4 head_feat4(const HeadParams& p, const float* f, int b, int k) {
+  if (!p.part) return *reinterpret_cast<const float4*>(f + k);
+  const float* pr = p.part + (size_t)b * p.S * p.K + k;
+  float4 a = __ldg(reinterpret_cast<const float4*>(pr));
+  for (int s = 1; s < p.S; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(pr + (size_t)s * p.K));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float4 bb = p.fc_bias ? __ldg(reinterpret_cast<const float4*>(p.fc_bias + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float vx = a.x + bb.x, vy = a.y + bb.y, vz = a.z + bb.z, vw = a.w + bb.w;
+  if (p.fc_tanh) return make_float4(tanhf(vx), tanhf(vy), tanhf(vz), tanhf(vw));
+  return make_float4(fmaxf(vx, vx * p.fc_slope), fmaxf(vy, vy * p.fc_slope), fmaxf(vz, vz * p.fc_slope),
+                     fmaxf(vw, vw * p.fc_slope));
+}
 
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float red[8];
@@ -685,7 +713,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   const float* f = p.feat + (size_t)b * p.K;
   float acc = 0.f;
   for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
-    const float4 a = *reinterpret_cast<const float4*>(f + k);
+    const float4 a = head_feat4(p, f, b, k);
     const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
     acc = fmaf(a.x, ww.x, acc);
     acc = fmaf(a.y, ww.y, acc);
@@ -733,7 +761,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     const float dl = 1.f / (1.f + expf(-logit)) - 1.f;
     float* d = p.dpre + (size_t)b * p.K;
     for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
-      const float4 a = *reinterpret_cast<const float4*>(f + k);
+      const float4 a = head_feat4(p, f, b, k);
       const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
       float4 o;
       o.x = dl * ww.x * act_grad_from_output(a.x, p.act);
@@ -876,6 +904,13 @@ static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
   w.total = off;
 }
 
+// The last hidden layer runs split-K and nothing but the head reads its output: the head kernel then adds the partial
+// sums itself and the activation is never written (CGS_DEBUG bit 131072 keeps the separate reduce kernel).
+static bool head_takes_partials(const Chain& c, const Workspace& w, int64_t B, int math) {
+  const cgs_layer_desc& L = c.layers[c.n - 1];
+  return use_fc_split(L, false, B, math, w.col) && !(debug_flags() & 131072) && cstride(L.cout) == c.head.cin;
+}
+
 static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st) {
   for (int i = 0; i < c.n; ++i) {
     PassEpi e;
@@ -894,7 +929,8 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
       if (rc < 0) return rc;
       if (rc == 1) { ++i; continue; }
     }
-    if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st)) return rc;
+    const bool defer = (i == c.n - 1) && head_takes_partials(c, w, B, math);
+    if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st, false, defer)) return rc;
   }
   return CGS_OK;
 }
@@ -958,8 +994,16 @@ extern "C" size_t cgs_refine_workspace_bytes(const cgs_net_desc* gtail, const cg
   return w.total + 256;
 }
 
-static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams hp, cudaStream_t st) {
+static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams hp, int math, cudaStream_t st) {
   hp.feat = w.act[c.n];
+  if (head_takes_partials(c, w, B, math)) {          // run_forward left the split-K partial sums in the scratch buffer
+    const cgs_layer_desc& L = c.layers[c.n - 1];
+    hp.part = w.col;
+    hp.S = fc_split(L, false);
+    hp.fc_bias = L.bias;
+    hp.fc_slope = L.act == ACT_RELU ? 0.f : (L.act == ACT_LRELU ? 0.2f : 1.f);
+    hp.fc_tanh = (L.act == ACT_TANH);
+  }
   hp.w = c.head.w_fwd;
   hp.bias = c.head.bias;
   hp.K = c.head.cin;
@@ -1047,7 +1091,7 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;
   hp.step = -1;
   hp.dpre = K > 0 ? w.g[0] : nullptr;
-  if (int rc = head_launch(c, w, Bact, hp, st)) return rc;
+  if (int rc = head_launch(c, w, Bact, hp, cfg->math, st)) return rc;
   ConvGemmParams upd;
   std::memset(&upd, 0, sizeof(upd));
   upd.sgd = cfg->method == CGS_POLICY_SGD;
@@ -1091,7 +1135,7 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
     if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;                   // :73
     hp.step = i;
     hp.dpre = (i + 1 < K) ? w.g[0] : nullptr;         // the gradient after the last step is never consumed
-    if (int rc = head_launch(c, w, Bact, hp, st)) return rc;                          // :76-83
+    if (int rc = head_launch(c, w, Bact, hp, cfg->math, st)) return rc;                          // :76-83
   }
   if (compacting && Bact > 0) {
     scatter_active_kernel<<<(unsigned)Bact, 128, 0, st>>>((const float4*)w.act[0], hp.orig, w.done, (float4*)feature_out,
@@ -1126,7 +1170,7 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   hp.step = -1;
   hp.round_out = (math == CGS_MATH_TF32_TENSOR);
   hp.dpre = grad_out ? w.g[0] : nullptr;
-  if (int rc = head_launch(c, w, B, hp, st)) return rc;
+  if (int rc = head_launch(c, w, B, hp, math, st)) return rc;
   cudaMemcpyAsync(logit_out, w.cur_logit, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
   if (img_out) {
     const cgs_layer_desc& Li = c.layers[c.n_gtail - 1];

@@ -193,7 +193,8 @@ def test_cuda_graph_replay_is_bit_identical(cgs_lib, cuda_device):
 
 
 def test_launch_and_lowering_knobs_do_not_change_results(cgs_lib, cuda_device):
-    """Programmatic dependent launch (bit 32768) reorders nothing: bit-identical.  The fc split-K lowering (off with
+    """Programmatic dependent launch (bit 32768) and where the split-K partial sums are added (head kernel or a separate
+    reduce kernel, bit 131072) change nothing: bit-identical.  The fc split-K lowering (off with
     bit 16384), the fused edge kernels (off with bit 4096) and their pairing into one kernel (off with bit 65536) only
     change summation order or nothing at all: same refined batch within the TF32 tolerance and the same best step for
     nearly every sample."""
@@ -214,8 +215,8 @@ def test_launch_and_lowering_knobs_do_not_change_results(cgs_lib, cuda_device):
             cgs_lib.cgs_debug_set_flags(old)
 
     base = run(0)
-    pdl = run(32768)
-    assert all(torch.equal(a, b) for a, b in zip(base, pdl))
+    for same in (32768, 131072):                             # PDL; separate split-K reduce kernel instead of the head's
+        assert all(torch.equal(a, b) for a, b in zip(base, run(same))), same
     for flags in (16384, 4096, 65536, 16384 | 4096):         # 65536: the two edge pairs as four separate kernels
         x, logit, step = run(flags)
         assert rel_l2(x.cpu().numpy(), base[0].cpu().numpy()) <= 1e-2
