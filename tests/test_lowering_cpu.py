@@ -59,3 +59,20 @@ def test_layer_forward_and_dgrad_lowering(cgs_lib, arch_name):
             gacc = emulate.layer_pass(layer, True, B, dyp, w_bwd.numpy())
             gref = dx.numpy().reshape(B, hin, win, cin)
             assert np.abs(gacc[..., :cin] - gref).max() <= 1e-4 * max(1.0, np.abs(gref).max()), (layer["name"], "bwd")
+
+
+def test_multiply_high_division_is_exact():
+    """csrc/conv_gemm.cuh fast_div: n // d == (n * ceil(2^64 / d)) >> 64 for every 32-bit n (magic 0 encodes d == 1).
+    The persistent tile index of every GEMM / edge kernel is decomposed with it, so it must be exact, not close."""
+    import random
+    rng = random.Random(7)
+    ds = [1, 2, 3, 4, 7, 8, 14, 25, 49, 98, 147, 148, 196, 1024, 1568, 2048, 65535, 65536, 1 << 20, (1 << 31) - 1]
+    ds += [rng.randrange(1, 1 << 31) for _ in range(200)]
+    for d in ds:
+        magic = 0 if d <= 1 else ((1 << 64) - 1) // d + 1
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 32) - 1] + [rng.randrange(0, 1 << 32) for _ in range(200)]
+        for n in ns:
+            if n < 0 or n >= (1 << 32):
+                continue
+            got = n if magic == 0 else (n * magic) >> 64
+            assert got == n // d, (n, d)
