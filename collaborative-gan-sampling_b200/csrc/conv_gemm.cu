@@ -77,7 +77,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a) {
@@ -402,18 +402,18 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       auto prefetch = [&](int ch) {
         const int n = n0 + ch * EPI_CH + c4 * 4;
         if (ch >= nch || n >= p.ON) return;
-        if (p.epi == EPI_BWD) {
+        if (EPI == EPI_BWD) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
             if (ro[ps] >= 0) x0[ps] = __ldg(reinterpret_cast<const float4*>(p.aux + ro[ps] + n));
-        } else if (p.epi == EPI_UPDATE) {
+        } else if (EPI == EPI_UPDATE) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
             if (ro[ps] >= 0) {
               x0[ps] = *reinterpret_cast<const float4*>(p.out + ro[ps] + n);
               if (!p.sgd && !p.first) x1[ps] = *reinterpret_cast<const float4*>(p.mom + ro[ps] + n);
             }
-        } else if (p.epi == EPI_FWD) {
+        } else if (EPI == EPI_FWD) {
           x0[0] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
@@ -461,7 +461,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           float4 o[PASSES];
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
-            if (ro[ps] >= 0 && n_ok) o[ps] = epilogue4(p, ro[ps] + n, a[ps], p.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
+            if (ro[ps] >= 0 && n_ok) o[ps] = epilogue4_t<EPI>(p, ro[ps] + n, a[ps], EPI == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
           if (warp == 0 && lane == 0) trace(p, 4, 1, tile_count * 8 + ch);
           if (!(p.debug & 2048)) prefetch(ch + chunk_groups);   // operands of the next chunk: overlap with these stores
 #pragma unroll
@@ -591,8 +591,8 @@ int pick_bn_for(const ConvGemmParams& p, int num_sms) {
   return bn;
 }
 
-template <int BN>
-int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
+template <int BN, int EPI>
+int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   using C = Cfg<BN>;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -660,7 +660,7 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -672,11 +672,21 @@ int launch_tc(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStre
   p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
   p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
   const int grid = total < num_sms ? total : num_sms;
-  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
+  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
+}
+
+template <int BN>
+int launch_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
+  switch (p.epi) {                          // the epilogue mode is compiled into the kernel
+    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD>(p, w, w_rows, w_cols, stream);
+    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD>(p, w, w_rows, w_cols, stream);
+    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE>(p, w, w_rows, w_cols, stream);
+    default: return launch_tc_epi<BN, EPI_RAW>(p, w, w_rows, w_cols, stream);
+  }
 }
 
 void derive_act(ConvGemmParams& p) {

@@ -107,10 +107,12 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 // Four consecutive output channels.  `off` = element offset in mom; x0 / x1 are the operands the caller has already
 // fetched (so that many loads can be in flight): FWD x0 = bias; BWD x0 = forward output of the differentiated layer;
-// UPDATE x0 = current feature, x1 = momentum.
-__device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, float4 a, float4 x0, float4 x1) {
+// UPDATE x0 = current feature, x1 = momentum.  EPI is a compile-time constant in the tensor-core kernel (the epilogue
+// runs per 64-byte row segment: no run-time mode switches there) and p.epi in the other callers.
+template <int EPI>
+__device__ __forceinline__ float4 epilogue4_t(const ConvGemmParams& p, int off, float4 a, float4 x0, float4 x1) {
   float4 o = a;
-  if (p.epi == EPI_FWD) {
+  if (EPI == EPI_FWD) {
     const float vx = a.x + x0.x, vy = a.y + x0.y, vz = a.z + x0.z, vw = a.w + x0.w;
     if (!p.act_tanh) {          // relu / lrelu / none: max(v, slope * v)
       o.x = fmaxf(vx, vx * p.slope); o.y = fmaxf(vy, vy * p.slope);
@@ -118,7 +120,7 @@ __device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, fl
     } else {
       o.x = tanhf(vx); o.y = tanhf(vy); o.z = tanhf(vz); o.w = tanhf(vw);
     }
-  } else if (p.epi == EPI_BWD) {
+  } else if (EPI == EPI_BWD) {
     if (!p.act_tanh) {          // derivative through the forward output: 1 where it is positive, slope elsewhere
       o.x = a.x * (x0.x > 0.f ? 1.f : p.slope); o.y = a.y * (x0.y > 0.f ? 1.f : p.slope);
       o.z = a.z * (x0.z > 0.f ? 1.f : p.slope); o.w = a.w * (x0.w > 0.f ? 1.f : p.slope);
@@ -126,7 +128,7 @@ __device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, fl
       o.x = a.x * (1.f - x0.x * x0.x); o.y = a.y * (1.f - x0.y * x0.y);
       o.z = a.z * (1.f - x0.z * x0.z); o.w = a.w * (1.f - x0.w * x0.w);
     }
-  } else if (p.epi == EPI_UPDATE) {
+  } else if (EPI == EPI_UPDATE) {
     // sampling/policy.py:27-37; separately rounded multiplies / adds like the reference's un-fused TF ops
     float4 m;
     m.x = __fmul_rn(p.rate, a.x); m.y = __fmul_rn(p.rate, a.y); m.z = __fmul_rn(p.rate, a.z); m.w = __fmul_rn(p.rate, a.w);
@@ -148,6 +150,15 @@ __device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, fl
   }
   if (p.round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
   return o;
+}
+
+__device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, float4 a, float4 x0, float4 x1) {
+  switch (p.epi) {
+    case EPI_FWD: return epilogue4_t<EPI_FWD>(p, off, a, x0, x1);
+    case EPI_BWD: return epilogue4_t<EPI_BWD>(p, off, a, x0, x1);
+    case EPI_UPDATE: return epilogue4_t<EPI_UPDATE>(p, off, a, x0, x1);
+    default: return epilogue4_t<EPI_RAW>(p, off, a, x0, x1);
+  }
 }
 
 // host launchers (conv_gemm.cu)
