@@ -359,6 +359,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const int chunk_groups = C::SPLIT_TILES ? 1 : ngroups;   // groups that share the chunks of one tile
     const int chunk_first = C::SPLIT_TILES ? 0 : group;
     float* stage = smem_epi + warp * 32 * EPI_PITCH;
+    const bool dbg_skip_epi = (p.debug & 16) != 0, dbg_skip_store = (p.debug & 1024) != 0, dbg_no_prefetch = (p.debug & 2048) != 0;
     const int c4 = lane % Q;
     const int rsub = lane / Q;
     // tile-invariant part of the row -> output offset map of the PASSES rows this lane stores
@@ -444,7 +445,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         for (int u = 0; u < MAXOWN; ++u) {
           const int ch = ch0 + u * chunk_groups;
           if (ch >= nch) break;
-          if (p.debug & 16) continue;                          // warp-uniform
+          if (dbg_skip_epi) continue;                          // warp-uniform
           // lane = row: stage 32 rows x 16 columns, then re-read with lane = (row group, 16-byte column)
 #pragma unroll
           for (int q4 = 0; q4 < Q; ++q4)
@@ -463,10 +464,10 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           for (int ps = 0; ps < PASSES; ++ps)
             if (ro[ps] >= 0 && n_ok) o[ps] = epilogue4_t<EPI>(p, ro[ps] + n, a[ps], EPI == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
           if (warp == 0 && lane == 0) trace(p, 4, 1, tile_count * 8 + ch);
-          if (!(p.debug & 2048)) prefetch(ch + chunk_groups);   // operands of the next chunk: overlap with these stores
+          if (!dbg_no_prefetch) prefetch(ch + chunk_groups);   // operands of the next chunk: overlap with these stores
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
-            if (ro[ps] >= 0 && n_ok && !(p.debug & 1024)) *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o[ps];
+            if (ro[ps] >= 0 && n_ok && !dbg_skip_store) *reinterpret_cast<float4*>(p.out + ro[ps] + n) = o[ps];
           if (warp == 0 && lane == 0) trace(p, 4, 2, tile_count * 8 + ch);
           __syncwarp();
           if (warp == 0 && lane == 0) trace(p, 4, 3, tile_count * 8 + ch);

@@ -712,8 +712,10 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   const int ob = p.orig ? p.orig[b] : b;           // where this sample's results live
   const float* f = p.feat + (size_t)b * p.K;
   float acc = 0.f;
+  float4 a_first = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's first four inputs, reused by the gradient pass
   for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
     const float4 a = head_feat4(p, f, b, k);
+    if (k < 256 * 4) a_first = a;
     const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
     acc = fmaf(a.x, ww.x, acc);
     acc = fmaf(a.y, ww.y, acc);
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     const float dl = 1.f / (1.f + expf(-logit)) - 1.f;
     float* d = p.dpre + (size_t)b * p.K;
     for (int k = threadIdx.x * 4; k < p.K; k += 256 * 4) {
-      const float4 a = head_feat4(p, f, b, k);
+      const float4 a = (k < 256 * 4) ? a_first : head_feat4(p, f, b, k);
       const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w + k));
       float4 o;
       o.x = dl * ww.x * act_grad_from_output(a.x, p.act);
