@@ -97,6 +97,50 @@ def gather_accepted(local_rows, src_global, bounds, group=None):
     return torch.cat([out[r * m:r * m + c] for r, c in enumerate(counts)])
 
 
+def gather_accepted_async(local_rows, emit_global, count, lo, hi, group=None):
+    """``gather_accepted`` with NO host synchronisation (device-resident counts).
+
+    ``emit_global`` [cap] int32 is the (padded) ascending list of emitted GLOBAL row ids and ``count`` [1] the number
+    of valid entries -- identical on every rank, because every rank evaluated the same global chain
+    (``IndependenceSampler.select_async`` on the gathered scores).  This rank owns global rows [lo, hi).
+    Every rank fills the positions whose source row it owns into a zero [cap, ...] buffer; ONE all-reduce(SUM) on the
+    int32 view of that buffer merges the disjoint contributions (integer addition of zero bits is exact, also for
+    -0.0 and NaN payloads), so the result is bit-identical to the single-GPU gather.  The payload is cap x row bytes
+    whatever the world size.  Returns (rows [cap, ...], count); rows past ``count`` are zero.
+    """
+    rank, ws = world()
+    cap = emit_global.numel()
+    pos = torch.arange(cap, device=emit_global.device)
+    src = emit_global.long()
+    mine = (pos < count.reshape(()).long()) & (src >= lo) & (src < hi)
+    n_local = local_rows.shape[0]
+    if n_local == 0:
+        out = torch.zeros((cap,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    else:
+        local_idx = (src - lo).clamp_(0, n_local - 1)
+        shape = (cap,) + (1,) * (local_rows.dim() - 1)
+        out = torch.where(mine.view(shape), local_rows[local_idx], torch.zeros((), dtype=local_rows.dtype,
+                                                                             device=local_rows.device))
+    if ws > 1:
+        out = out.contiguous()
+        dist.all_reduce(out.view(torch.int32) if out.dtype == torch.float32 else out, op=dist.ReduceOp.SUM, group=group)
+    return out, count
+
+
+def reduce_stats_async(n_accepted, score_sum, score_max, group=None):
+    """Acceptance / score statistics as ONE device tensor [3] = (sum n, sum score, max score), float64; no host sync
+    (``n_accepted`` may be a device tensor).  One all_gather of 24 bytes per rank."""
+    rank, ws = world()
+    dev = score_sum.device
+    mine = torch.stack([torch.as_tensor(v, device=dev).to(torch.float64).reshape(()) for v in (n_accepted, score_sum, score_max)])
+    if ws == 1:
+        return mine
+    allv = torch.empty(ws * 3, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.view(ws, 3)
+    return torch.stack([allv[:, 0].sum(), allv[:, 1].sum(), allv[:, 2].max()])
+
+
 def reduce_stats(n_accepted, score_sum, score_max, group=None):
     """(sum, sum, max) all-reduce of the acceptance / score statistics; returns python floats."""
     rank, ws = world()

@@ -268,6 +268,25 @@ class NetSpec:
         self.d = PackedNet(arch["d"], "discriminator", weights, self.device, math)
         self.role = role
 
+    @classmethod
+    def from_variables(cls, arch, variables, device="cuda", math="tf32", layout="tf"):
+        """Build a spec from an externally produced name -> array mapping: Saver decorations are
+        stripped, ``layout='torch'`` converts PyTorch-ordered kernels, and every variable is checked against the
+        architecture (missing names / wrong layouts raise with the offending name)."""
+        from . import weights as W
+        v = W.normalize_names(variables)
+        if layout == "torch":
+            v = W.from_torch_layout(arch, v)
+        elif layout != "tf":
+            raise ValueError("layout must be 'tf' or 'torch'")
+        return cls(arch, W.validate(arch, v), device, math=math)
+
+    @classmethod
+    def from_npz(cls, arch, path, device="cuda", math="tf32", layout="tf"):
+        """Spec from an ``.npz`` of the reference's TF variables (``cgs.weights`` says how to dump a checkpoint)."""
+        from . import weights as W
+        return cls.from_variables(arch, W.load_npz(path), device, math=math, layout=layout)
+
     @property
     def feature_shape(self):
         return tuple(self.arch["feature_shape"])

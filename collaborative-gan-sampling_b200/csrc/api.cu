@@ -27,6 +27,24 @@ int debug_flags() {
 }
 void set_debug_flags(int v) { g_debug.store(v < 0 ? 0 : v, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+int device_num_sms() {
+  static std::atomic<int> cache[kMaxDevices];     // zero-initialised; 0 = not queried yet
+  const int dev = current_device();
+  if (dev >= 0 && dev < kMaxDevices) {
+    const int v = cache[dev].load(std::memory_order_relaxed);
+    if (v) return v;
+  }
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev < kMaxDevices) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 int require_sm100() {
   static thread_local int cached_dev = -1;
   static thread_local int cached_ok = 0;

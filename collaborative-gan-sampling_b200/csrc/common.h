@@ -1,7 +1,9 @@
 // Shared host-side helpers: status codes, thread-local error message, CUDA error capture.
 #pragma once
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "cgs.h"
@@ -26,6 +28,31 @@ inline int check_launch(const char* what) {
 
 // The product never runs on anything but sm_100: refuse loudly instead of falling back.
 int require_sm100();
+
+// Per-device facts and one-time kernel attributes.  cudaFuncSetAttribute and the SM count are PER DEVICE: a process
+// that drives several GPUs (or several host threads) must not share one cached flag, so every cache below is indexed
+// by the current device and guarded.
+constexpr int kMaxDevices = 64;
+int current_device();               // cudaGetDevice, -1 on error
+int device_num_sms();               // multiprocessor count of the current device (cached per device, api.cu)
+
+struct DynSmemCache {               // one per kernel instantiation (function-local static)
+  std::mutex m;
+  std::atomic<size_t> set[kMaxDevices];
+  DynSmemCache() { for (auto& v : set) v.store(0, std::memory_order_relaxed); }
+};
+// Opt the kernel in to `smem` bytes of dynamic shared memory on the current device (idempotent, grows only).
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, size_t smem, DynSmemCache& c) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (c.set[dev].load(std::memory_order_acquire) >= smem) return cudaSuccess;
+  std::lock_guard<std::mutex> lock(c.m);
+  if (c.set[dev].load(std::memory_order_relaxed) >= smem) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) c.set[dev].store(smem, std::memory_order_release);
+  return e;
+}
 
 // Developer knobs: env CGS_DEBUG at first use, overridable with cgs_debug_set_flags (api.cu).
 int debug_flags();

@@ -123,8 +123,12 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   pdl_launch_dependents();
   pdl_wait();
 
-  const int tiles_per_class = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_per_class * p.nclasses;
+  // tile counts follow the images still in the batch (device-resident count in early-exit mode, else p.B)
+  const LiveTiles lt = live_tiles(p);
+  const int tiles_per_class = lt.tiles_per_class;
+  const int total_tiles = lt.total;
+  const unsigned long long fd_tpc = lt.fd_tiles_per_class;
+  const int B_live = lt.B;
   const int rows_per_img_tile = p.BH * p.MW;   // rows one image contributes to a tile
 
   if (warp >= kEpiWarps && warp < kMmaWarp && !p.a_tma) {
@@ -162,7 +166,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const int i = q - hh * p.MW;
         const int b = (m_tile / p.hy_tiles) * p.BB + bb;
         const int j = (m_tile % p.hy_tiles) * p.BH + hh;
-        if (r < p.rows_valid && b < p.B && j < p.MH) {
+        if (r < p.rows_valid && b < B_live && j < p.MH) {
           const int y0 = j * p.S, x0 = i * p.S;
           rbase[it] = ((b * p.IH + y0) * p.IW + x0) * p.Cs;
           uint32_t mx = 0;
@@ -225,7 +229,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       uint32_t stage = 0, phase = 0;
       const bool skip = (p.debug & 2) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ci = fast_div(tile, p.fd_tiles_per_class);
+        const int ci = fast_div(tile, fd_tpc);
         const int rem = tile - ci * tiles_per_class;
         const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
         const int katom0 = p.cls[ci].k0 / BK;
@@ -254,7 +258,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const bool skip = (p.debug & 8) != 0;
         const int cblocks = p.cblocks;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          const int ci = fast_div(tile, p.fd_tiles_per_class);
+          const int ci = fast_div(tile, fd_tpc);
           const int rem = tile - ci * tiles_per_class;
           const int m_tile = fast_div(rem, p.fd_n_tiles);
           const GemmClass& gc = p.cls[ci];
@@ -307,7 +311,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const bool a_tma = p.a_tma != 0;
     const bool skip_mma = (p.debug & 4) != 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
-      const int ci = fast_div(tile, p.fd_tiles_per_class);
+      const int ci = fast_div(tile, fd_tpc);
       const int nkb = p.cls[ci].nkb;
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
@@ -365,7 +369,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // tile-invariant part of the row -> output offset map of the PASSES rows this lane stores
     // (a tile spans either several whole images, BB > 1, or part of one image, BB == 1: one bound test per row)
     const bool multi_img = p.BB > 1;
-    const int lim = multi_img ? p.B : p.MH;
+    const int lim = multi_img ? B_live : p.MH;
     int l_off[PASSES], l_pos[PASSES];
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
@@ -380,7 +384,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     for (uint32_t tile_count = C::SPLIT_TILES ? group : 0;; tile_count += tile_groups) {
       const int tile = blockIdx.x + tile_count * gridDim.x;
       if (tile >= total_tiles) break;
-      const int ci = fast_div(tile, p.fd_tiles_per_class);
+      const int ci = fast_div(tile, fd_tpc);
       const int rem = tile - ci * tiles_per_class;
       const int m_tile = fast_div(rem, p.fd_n_tiles);
       const int n_tile = rem - m_tile * p.n_tiles;
@@ -488,13 +492,19 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 __global__ void __launch_bounds__(256)
 conv_gemm_simt_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ w, int w_cols) {
   const int ngroups = p.ON / 4;
-  const long long total = (long long)p.nclasses * p.M * ngroups;
+  int M_live = p.M;
+  if (p.live) {                                   // early exit: rows of the images still in the batch
+    const int b = *reinterpret_cast<const volatile int*>(p.live);
+    const long long m = (long long)(b < 0 ? 0 : b) * p.MH * p.MW;
+    if (m < M_live) M_live = (int)m;
+  }
+  const long long total = (long long)p.nclasses * M_live * ngroups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int ng = (int)(idx % ngroups);
     const long long t = idx / ngroups;
-    const int m = (int)(t % p.M);
-    const int ci = (int)(t / p.M);
+    const int m = (int)(t % M_live);
+    const int ci = (int)(t / M_live);
     const GemmClass& gc = p.cls[ci];
     const int per_img = p.MH * p.MW;
     const int b = m / per_img;
@@ -653,18 +663,11 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (ra != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (A operand) failed (%d)", (int)ra);
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
+  const int num_sms = device_num_sms();
+  {
+    static DynSmemCache smem_cache;            // per kernel instantiation, per device
+    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI>, (size_t)C::SMEM_BYTES, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const long long total_ll = (long long)p.m_tiles * p.n_tiles * p.nclasses;
   if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
@@ -724,12 +727,7 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
   derive_act(p);
   if (int rc = validate(p, w_cols)) return rc;
   if (p.M <= 0) return CGS_OK;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_num_sms();
   int bn = p.force_bn ? p.force_bn : pick_bn_for(p, num_sms);
   {
     static int force = -1;                    // developer knob: CGS_FORCE_BN=16..256 overrides the tile-width heuristic

@@ -68,6 +68,10 @@ struct ConvGemmParams {
   int act_tanh;       // act == tanh (slow path)
   int round_out;      // round results to TF32 (RN) because the next consumer is a kind::tf32 MMA
   int force_bn;       // 0 = tile-width heuristic, else the BN instance to launch
+  // early exit (device-resident batch size): when non-null, only the first *live images are processed -- tiles past
+  // them are never scheduled, rows past them never stored.  Grids stay sized for the full batch, so the launch
+  // sequence is static (CUDA-graph capturable) and no host synchronisation is needed when samples leave the batch.
+  const int* live;
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
   // exact division of the persistent tile index by multiply-shift (filled by the launcher; see fast_div)
   unsigned long long fd_tiles_per_class, fd_n_tiles, fd_hy_tiles;
@@ -97,6 +101,29 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
 inline unsigned long long fast_div_magic(unsigned d) { return d <= 1 ? 0ull : (~0ull) / d + 1ull; }
 __device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
   return magic ? (int)__umul64hi((unsigned long long)(unsigned)n, magic) : n;
+}
+__device__ __forceinline__ unsigned long long fast_div_magic_dev(unsigned d) { return d <= 1 ? 0ull : (~0ull) / d + 1ull; }
+
+// Tile counts of a launch for the images that are still in the batch (ConvGemmParams::live).
+struct LiveTiles {
+  int B, tiles_per_class, total;
+  unsigned long long fd_tiles_per_class;
+};
+__device__ __forceinline__ LiveTiles live_tiles(const ConvGemmParams& p) {
+  LiveTiles t;
+  if (!p.live) {
+    t.B = p.B;
+    t.tiles_per_class = p.m_tiles * p.n_tiles;
+    t.fd_tiles_per_class = p.fd_tiles_per_class;
+  } else {
+    int b = *reinterpret_cast<const volatile int*>(p.live);
+    b = b < 0 ? 0 : (b > p.B ? p.B : b);
+    t.B = b;
+    t.tiles_per_class = ((b + p.BB - 1) / p.BB) * p.hy_tiles * p.n_tiles;
+    t.fd_tiles_per_class = fast_div_magic_dev((unsigned)t.tiles_per_class);
+  }
+  t.total = t.tiles_per_class * p.nclasses;
+  return t;
 }
 
 __device__ __forceinline__ float tf32_rn(float x) {

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4) edge_wide_kernel(const EdgeWide
 
   pdl_launch_dependents();
   pdl_wait();                                // tables and weights above are constants; activations from here on
+  if (p.e.live) ntiles = min(ntiles, live_images(p.e.live, ntiles / bands) * bands);
   int tile = blockIdx.x;
   if (tile < ntiles) stage_patch(tile, 0);
   cp_async_commit();
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(EN_THREADS) edge_narrow_kernel(const EdgeNarro
   __syncthreads();
   pdl_launch_dependents();
   pdl_wait();                                // weights above are constants; activations from here on
+  if (p.e.live) ntiles = min(ntiles, live_images(p.e.live, p.B) * p.bands);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = tile / p.bands;
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(EN_THREADS, 4) edge_pair_kernel(const EdgeNarr
   pdl_launch_dependents();
   pdl_wait();
   const int npx = pw.OH * pw.OW;
-  for (int b = blockIdx.x; b < pn.B; b += gridDim.x) {
+  const int B_live = live_images(pw.e.live, pn.B);
+  for (int b = blockIdx.x; b < B_live; b += gridDim.x) {
     narrow_mma<NT>(pn.in + (size_t)b * pn.IH * pn.IW * pn.K, pn.K, pn.IH * pn.IW, bfrag_n, col_s);
     __syncthreads();
     narrow_col2im<NT, CI>(pn, col_s, b, 0, pn.IH, 0, pn.OH, store_image ? pn.out : nullptr, patch4, pw.pad_y);
@@ -422,28 +425,19 @@ __global__ void __launch_bounds__(EN_THREADS, 4) edge_pair_kernel(const EdgeNarr
   }
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
+int num_sms() { return device_num_sms(); }
 
 template <int NT, int CI>
 int launch_narrow_nt(const EdgeNarrowParams& p, cudaStream_t st) {
   constexpr int CP = NT * 8 + 4;
   constexpr size_t smem = (size_t)EN_KSTEPS * NT * 32 * sizeof(float2) + (size_t)EN_ROWS * CP * sizeof(float);
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(edge_narrow_kernel<NT, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int ctas_per_sm = 0;
+  {
+    static DynSmemCache smem_cache;
+    cudaError_t e = ensure_dyn_smem(edge_narrow_kernel<NT, CI>, smem, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_narrow): %s", cudaGetErrorString(e));
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, edge_narrow_kernel<NT, CI>, EN_THREADS, smem);
-    if (e != cudaSuccess || n < 1) return set_error(CGS_ERR_CUDA, "edge_narrow occupancy query failed");
-    ctas_per_sm = n;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, edge_narrow_kernel<NT, CI>, EN_THREADS, smem);
+    if (e != cudaSuccess || ctas_per_sm < 1) return set_error(CGS_ERR_CUDA, "edge_narrow occupancy query failed");
   }
   const long long tiles = (long long)p.B * p.bands;
   if (tiles >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large; split the batch");
@@ -476,11 +470,10 @@ int launch_wide_mode(const EdgeWideParams& p, int B, cudaStream_t st) {
   const int PR = 2 * RO + p.k - 2;
   size_t smem = (size_t)ksteps * EW_NT * 32 * sizeof(float2) + (size_t)2 * PR * p.pitch * sizeof(float4);
   if (smem > 200 * 1024) return set_error(CGS_ERR_UNSUPPORTED, "edge_wide: image band does not fit shared memory");
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(edge_wide_kernel<MODE, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    static DynSmemCache smem_cache;
+    cudaError_t e = ensure_dyn_smem(edge_wide_kernel<MODE, ROUND>, smem, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_wide): %s", cudaGetErrorString(e));
-    smem_set = smem;
   }
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_wide_kernel<MODE, ROUND>, EW_THREADS, smem);
@@ -545,11 +538,10 @@ int launch_pair_inst(const EdgeNarrowParams& pn, const EdgeWideParams& pw, int s
   const int col_rows = ((pn.IH * pn.IW + 15) / 16) * 16;
   const size_t smem = (size_t)EN_KSTEPS * NT * 32 * sizeof(float2) + (size_t)ksteps_w * EW_NT * 32 * sizeof(float2) +
                       (size_t)PR * pw.pitch * sizeof(float4) + (size_t)col_rows * CP * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(edge_pair_kernel<NT, CI, MODE, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    static DynSmemCache smem_cache;
+    cudaError_t e = ensure_dyn_smem(edge_pair_kernel<NT, CI, MODE, ROUND>, smem, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_pair): %s", cudaGetErrorString(e));
-    smem_set = smem;
   }
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_pair_kernel<NT, CI, MODE, ROUND>, EN_THREADS, smem);

@@ -22,7 +22,15 @@ struct EdgeEpi {
   const float* bias;
   const float* aux;
   float* mom;
+  const int* live;    // early exit: device-resident number of images still in the batch (null = all of them)
 };
+
+// images a kernel of the chain has to process (grids stay sized for the full batch; see ConvGemmParams::live)
+__device__ __forceinline__ int live_images(const int* live, int B) {
+  if (!live) return B;
+  const int b = *reinterpret_cast<const volatile int*>(live);
+  return b < 0 ? 0 : (b > B ? B : b);
+}
 
 struct EdgeWideParams {
   const float* in;    // pitched image-like tensor

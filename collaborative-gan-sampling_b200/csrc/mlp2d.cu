@@ -227,7 +227,7 @@ mlp2d_refine_kernel(const cgs_mlp_desc d, PolicyConsts pc, int steps, float inv_
 int check_mlp(const cgs_mlp_desc* d) {
   if (!d) return set_error(CGS_ERR_INVALID, "null mlp descriptor");
   if (d->nhidden != H) return set_error(CGS_ERR_UNSUPPORTED, "nhidden %d: this build keeps the MLP in shared memory for nhidden == 64 only", d->nhidden);
-  if (d->nlayers < 3 || d->nlayers > CGS_MLP_MAX_LAYERS) return set_error(CGS_ERR_UNSUPPORTED, "nlayers %d (3..8)", d->nlayers);
+  if (d->nlayers < 2 || d->nlayers > CGS_MLP_MAX_LAYERS) return set_error(CGS_ERR_UNSUPPORTED, "nlayers %d (2..8)", d->nlayers);   // synthetic/GAN.py:32 range(nlayers-2)
   for (int l = 0; l < d->nlayers; ++l)
     if (!d->weights[l] || !d->biases[l]) return set_error(CGS_ERR_INVALID, "null weights for layer %d", l);
   return CGS_OK;

@@ -365,10 +365,16 @@ struct Col2imParams {
   int epi, act, round_out;
   int out_pitch, out_xoff;   // row pitch (pixels) and first data column of out / aux (dense: OW, 0)
   long long pixels;          // B * OH * out_pitch (pad columns are written as zeros)
+  const int* live;           // early exit: images still in the batch (null = all)
 };
 
 __global__ void __launch_bounds__(256) col2im_kernel(const Col2imParams p) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.pixels;
+  long long pixels = p.pixels;
+  if (p.live) {
+    const long long per_img = (long long)p.OH * p.out_pitch;
+    pixels = (long long)live_images(p.live, (int)(p.pixels / per_img)) * per_img;
+  }
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < pixels;
        idx += (long long)gridDim.x * blockDim.x) {
     const int xc = (int)(idx % p.out_pitch);
     const long long t = idx / p.out_pitch;
@@ -416,6 +422,7 @@ struct PassEpi {
   const float* aux = nullptr;
   int round_out = 0;
   const ConvGemmParams* upd = nullptr;   // EPI_UPDATE fields
+  const int* live = nullptr;             // early exit: device-resident count of the images still in the batch
 };
 
 // Epilogue description of an image-edge kernel (edge_conv.cuh) from the pass epilogue.
@@ -428,6 +435,7 @@ EdgeEpi make_edge_epi(const PassEpi& e, const float* bias) {
   x.round_out = e.round_out;
   x.bias = (e.epi == EPI_FWD) ? bias : nullptr;
   x.aux = e.aux;
+  x.live = e.live;
   if (e.upd) {
     x.epi = EPI_UPDATE;
     x.mom = e.upd->mom; x.first = e.upd->first; x.sgd = e.upd->sgd; x.rate = e.upd->rate; x.alpha = e.upd->alpha;
@@ -452,6 +460,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   pdl_launch_dependents();
   pdl_wait();
   const int groups = p.ON / 4;
+  if (p.live) total4 = (long long)live_images(p.live, (int)(total4 / groups)) * groups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long b = idx / groups;
@@ -561,6 +570,8 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     }
     ConvGemmParams p;
     if (int rc = make_scatter_gemm_params(L, backward, B, in, col, p)) return rc;
+    // (early exit: the 1-tap GEMM over pixels runs over the full batch -- its rows are pixels, not images; the
+    //  col2im below stops at the live images)
     if (int rc = launch_gemm(p, w, rows, cols, math, st)) return rc;
     const LayerShape s = layer_shape(L);
     Col2imParams c;
@@ -583,6 +594,7 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     c.out_pitch = dense_image ? c.OW : img_pitch(c.OW);
     c.out_xoff = dense_image ? 0 : IMG_XOFF;
     c.pixels = (long long)B * c.OH * c.out_pitch;
+    c.live = e.live;
     long long blocks = (c.pixels + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     col2im_kernel<<<(int)blocks, 256, 0, st>>>(c); count_launch();
@@ -603,6 +615,8 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     }
     p.bias = nullptr;
     p.epi = EPI_RAW;
+    p.live = e.live;
+    pe.live = e.live;
     p.nclasses = S;
     p.cblocks = L.cin / 32 / S;
     for (int c = 0; c < S; ++c) {
@@ -635,6 +649,7 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
   p.act = e.act;
   p.aux = e.aux;
   p.round_out = e.round_out;
+  p.live = e.live;
   if (e.upd) {
     p.epi = EPI_UPDATE;
     p.mom = e.upd->mom; p.first = e.upd->first; p.sgd = e.upd->sgd; p.rate = e.upd->rate; p.alpha = e.upd->alpha;
@@ -683,6 +698,7 @@ struct HeadParams {
   const float* fc_bias;
   float fc_slope;       // relu 0, lrelu 0.2, none 1 (same expression as the GEMM epilogue: bit-identical)
   int fc_tanh;
+  const int* live;      // early exit: device-resident count of the rows still in the batch (null = gridDim.x)
 };
 
 // Input of the head for elements k..k+3 of sample b: the stored activation, or the split-K partial sums added in
@@ -709,6 +725,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
+  if (p.live && b >= *reinterpret_cast<const volatile int*>(p.live)) return;   // row left the batch (early exit)
   const int ob = p.orig ? p.orig[b] : b;           // where this sample's results live
   const float* f = p.feat + (size_t)b * p.K;
   float acc = 0.f;
@@ -795,21 +812,76 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   }
 }
 
-// rows still active (not done) -> flags for the ordered compaction
-__global__ void active_flags_kernel(const unsigned char* __restrict__ done, unsigned char* __restrict__ flags, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flags[i] = done[i] ? 0 : 1;
+// ---------------------------------------------------------------------------------------------
+// Early exit (README.md:13; opt-in, the reference itself always runs K steps: collaborator.py:63-83), device side.
+// After every fused policy step the rows D already classifies as real leave the batch: ONE single-CTA kernel turns the
+// per-row exit flags into the ordered list of the rows that stay and their count (ballot + warp-sum scan), ONE kernel
+// gathers feature / momentum / row-map rows through that list.  The count lives in device memory and every later
+// launch of the step reads it (ConvGemmParams::live and friends), so there is no host synchronisation, the launch
+// sequence is static and the whole K loop can be captured in a CUDA graph.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) live_compact_kernel(unsigned char* __restrict__ done, const int* __restrict__ live_in,
+                                                            int B, int* __restrict__ idx, int* __restrict__ live_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int s_base;
+  const int live = min(max(*live_in, 0), B);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < B; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool keep = i < live && !done[i];
+    if (i < B) done[i] = 0;                               // rows are renumbered: the flags start afresh
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_sums[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int w2 = 0; w2 < warp; ++w2) before += warp_sums[w2];
+    if (keep) idx[before + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = s_base;
+      for (int w2 = 0; w2 < 32; ++w2) t += warp_sums[w2];
+      s_base = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *live_out = s_base;
+}
+
+// rows idx[0 .. *count) of (feature, momentum, row map) -> rows 0 .. *count of the partner buffers (ordered)
+__global__ void __launch_bounds__(256) live_gather_kernel(const float4* __restrict__ feat_src, float4* __restrict__ feat_dst,
+                                                          const float4* __restrict__ mom_src, float4* __restrict__ mom_dst,
+                                                          const int* __restrict__ orig_src, int* __restrict__ orig_dst,
+                                                          const int* __restrict__ idx, const int* __restrict__ count,
+                                                          int elems4) {
+  const int rows = *count;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int s = idx[r];
+    const float4* fs = feat_src + (size_t)s * elems4;
+    float4* fd = feat_dst + (size_t)r * elems4;
+    for (int i = threadIdx.x; i < elems4; i += blockDim.x) fd[i] = fs[i];
+    if (mom_src) {
+      const float4* ms = mom_src + (size_t)s * elems4;
+      float4* md = mom_dst + (size_t)r * elems4;
+      for (int i = threadIdx.x; i < elems4; i += blockDim.x) md[i] = ms[i];
+    }
+    if (threadIdx.x == 0) orig_dst[r] = orig_src[s];
+  }
 }
 // feature rows of the samples that never exited -> their slot in the caller's buffer
 __global__ void scatter_active_kernel(const float4* __restrict__ feat, const int* __restrict__ orig,
-                                      const unsigned char* __restrict__ done, float4* __restrict__ out, int elems4) {
+                                      const unsigned char* __restrict__ done, const int* __restrict__ live,
+                                      float4* __restrict__ out, int elems4) {
   const int b = blockIdx.x;
-  if (done[b]) return;
+  if (b >= *live || done[b]) return;
   const float4* s = feat + (size_t)b * elems4;
   float4* d = out + (size_t)orig[b] * elems4;
   for (int i = threadIdx.x; i < elems4; i += blockDim.x) d[i] = s[i];
 }
-__global__ void iota_kernel(int* p, int n) {
+__global__ void iota_kernel(int* p, int n, int* live) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+  if (live && blockIdx.x == 0 && threadIdx.x == 0) *live = n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -872,14 +944,13 @@ struct Workspace {
   float* col;
   float* cur_logit;
   unsigned char* done;
-  // early-exit compaction: second feature / momentum buffers, row maps, flags, index list, counters
+  // early-exit compaction: ping-pong feature / momentum buffers, row maps, index list, the two live-row counters
   float* feat2;
+  float* feat3;
   float* mom2;
   int* orig[2];
-  unsigned char* flags;
   int* idx;
-  int* count;
-  int* bcounts;
+  int* count;            // count[0], count[1]: live rows, ping-pong per step
   size_t total;
 };
 
@@ -896,13 +967,12 @@ static void carve(const Chain& c, int64_t B, void* base, Workspace& w) {
   w.cur_logit = (float*)take((size_t)B * 4);
   w.done = (unsigned char*)take((size_t)B);
   w.feat2 = (float*)take((size_t)B * c.act_elems[0] * 4);
+  w.feat3 = (float*)take((size_t)B * c.act_elems[0] * 4);
   w.mom2 = (float*)take((size_t)B * c.act_elems[0] * 4);
   w.orig[0] = (int*)take((size_t)B * 4);
   w.orig[1] = (int*)take((size_t)B * 4);
-  w.flags = (unsigned char*)take((size_t)B);
   w.idx = (int*)take((size_t)B * 4);
   w.count = (int*)take(16);
-  w.bcounts = (int*)take((size_t)(B / 1024 + 2) * 4);
   w.total = off;
 }
 
@@ -913,9 +983,11 @@ static bool head_takes_partials(const Chain& c, const Workspace& w, int64_t B, i
   return use_fc_split(L, false, B, math, w.col) && !(debug_flags() & 131072) && cstride(L.cout) == c.head.cin;
 }
 
-static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st) {
+static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st,
+                       const int* live = nullptr) {
   for (int i = 0; i < c.n; ++i) {
     PassEpi e;
+    e.live = live;
     e.epi = EPI_FWD;
     e.act = c.layers[i].act;
     // TF32 path: activations that feed another MMA are rounded to TF32 (RN) where they are produced, so the
@@ -924,6 +996,7 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
     if (i == c.n_gtail - 1 && i + 1 < c.n) {
       // generator's last deconv + discriminator's first conv on the same image: one kernel when the shapes allow
       PassEpi e2;
+      e2.live = live;
       e2.epi = EPI_FWD;
       e2.act = c.layers[i + 1].act;
       e2.round_out = (math == CGS_MATH_TF32_TENSOR) && (i + 1 != c.n - 1);
@@ -940,11 +1013,12 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
 // Backward from dpre[c.n-1] (already in w.g[0]) down to the feature.  `upd` != null fuses the policy step into
 // the last GEMM's epilogue; otherwise the raw gradient is written to grad_out.
 static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math, const ConvGemmParams* upd,
-                        float* grad_out, cudaStream_t st) {
+                        float* grad_out, cudaStream_t st, const int* live = nullptr) {
   int cur = 0;
   for (int i = c.n - 1; i >= 0; --i) {
     float* dst = (i == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
     PassEpi e;
+    e.live = live;
     if (i > 0) {
       e.epi = EPI_BWD;
       e.aux = w.act[i];
@@ -956,6 +1030,7 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
     if (i == c.n_gtail && i >= 1) {
       // data-gradients of D's first conv and G's last deconv: one kernel, the image gradient never leaves the SM
       PassEpi e2;
+      e2.live = live;
       float* dst2 = (i - 1 == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
       if (i - 1 > 0) {
         e2.epi = EPI_BWD;
@@ -1073,27 +1148,25 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   if (compacting && cfg->mode != CGS_MODE_DETERMINISTIC)
     return set_error(CGS_ERR_UNSUPPORTED, "early exit is defined for the deterministic mode only");
   float* feature_out = feature;             // the caller's buffer: final state of every sample ends up here
-  int64_t Bact = B;                         // rows currently in the batch
-  int cur = 0;                              // which orig[] map is live
+  float* mom_cur = w.mom;
+  float* mom_alt = w.mom2;
+  const int* live = nullptr;                // device-resident count of the rows still in the batch (early exit)
+  int cur = 0;                              // which orig[] map / live counter is current
   if (compacting) {
-    // work on a private copy so that exited samples can be dropped and the rest compacted
+    // work on a private copy so that exited samples can be dropped and the rest compacted (ping-pong feat2 / feat3)
     cudaMemcpyAsync(w.feat2, feature, (size_t)B * c.act_elems[0] * 4, cudaMemcpyDeviceToDevice, st);
     w.act[0] = w.feat2;
-    iota_kernel<<<148, 256, 0, st>>>(w.orig[0], (int)B); count_launch();
+    iota_kernel<<<148, 256, 0, st>>>(w.orig[0], (int)B, w.count); count_launch();
     hp.orig = w.orig[0];
     hp.final_feature = feature_out;
+    live = w.count;
+    hp.live = live;
   }
-  float* feat_alt = feature;                // ping-pong partner of the private copy (safe: final rows are written
-  float* mom_cur = w.mom;                   // to feature_out only by rows that leave, see below)
-  float* mom_alt = w.mom2;
-  // NOTE: with compaction the caller's buffer doubles as the scatter target, so the ping-pong partner must be a
-  // separate allocation: use the momentum spare for features is not possible -> dedicated buffers
-  (void)feat_alt;
   // initial evaluation: collaborator.py:48-60
-  if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;
+  if (int rc = run_forward(c, w, B, cfg->math, st, live)) return rc;
   hp.step = -1;
   hp.dpre = K > 0 ? w.g[0] : nullptr;
-  if (int rc = head_launch(c, w, Bact, hp, cfg->math, st)) return rc;
+  if (int rc = head_launch(c, w, B, hp, cfg->math, st)) return rc;
   ConvGemmParams upd;
   std::memset(&upd, 0, sizeof(upd));
   upd.sgd = cfg->method == CGS_POLICY_SGD;
@@ -1102,46 +1175,39 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
   upd.clip = cfg->clip;
   upd.vmin = cfg->vmin;
   upd.vmax = cfg->vmax;
+  const int elems4 = (int)(c.act_elems[0] / 4);
   for (int i = 0; i < K; ++i) {                       // collaborator.py:63-83
     upd.first = (i == 0);
     upd.mom = mom_cur;
-    if (int rc = run_backward(c, w, Bact, cfg->math, &upd, nullptr, st)) return rc;   // grad + policy step (:66-70)
+    if (int rc = run_backward(c, w, B, cfg->math, &upd, nullptr, st, live)) return rc;   // grad + policy step (:66-70)
     if (compacting) {
       // drop the samples D already classifies as real (README.md:13): ordered compaction of the rows that stay.
       // Only the feature map, its momentum and the row map are live here (activations / gradients are dead).
-      active_flags_kernel<<<148, 256, 0, st>>>(w.done, w.flags, (int)Bact); count_launch();
-      if (int rc = compact_flags(w.flags, Bact, w.bcounts, w.idx, w.count, st)) return rc;
-      int n_active = 0;
-      cudaMemcpyAsync(&n_active, w.count, 4, cudaMemcpyDeviceToHost, st);
-      cudaError_t e = cudaStreamSynchronize(st);      // the one host sync of this opt-in mode: grid sizes follow
-      if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "early-exit sync: %s", cudaGetErrorString(e));
-      if (n_active == 0) { Bact = 0; break; }
-      if (n_active < Bact) {
-        float* feat_src = w.act[0];
-        float* feat_dst = (feat_src == w.feat2) ? w.g[1] : w.feat2;      // g[1] is dead between backward and forward
-        const size_t row_bytes = c.act_elems[0] * 4;
-        if (int rc = gather_rows(feat_src, (long)row_bytes, w.idx, w.count, n_active, feat_dst, st)) return rc;
-        if (!upd.sgd)
-          if (int rc = gather_rows(mom_cur, (long)row_bytes, w.idx, w.count, n_active, mom_alt, st)) return rc;
-        if (int rc = gather_rows(w.orig[cur], 4, w.idx, w.count, n_active, w.orig[cur ^ 1], st)) return rc;
-        if (feat_dst != w.feat2)                       // keep the live copy in feat2 (g[1] is about to be reused)
-          cudaMemcpyAsync(w.feat2, feat_dst, (size_t)n_active * row_bytes, cudaMemcpyDeviceToDevice, st);
-        w.act[0] = w.feat2;
-        float* t = mom_cur; mom_cur = mom_alt; mom_alt = t;
-        cur ^= 1;
-        hp.orig = w.orig[cur];
-        cudaMemsetAsync(w.done, 0, (size_t)n_active, st);
-        Bact = n_active;
-      }
+      // Everything is sized by the device-side counter: no host read-back, static launch sequence.
+      int* live_next = w.count + (cur ^ 1);
+      live_compact_kernel<<<1, 1024, 0, st>>>(w.done, live, (int)B, w.idx, live_next); count_launch();
+      float* feat_src = w.act[0];
+      float* feat_dst = (feat_src == w.feat2) ? w.feat3 : w.feat2;
+      const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
+      live_gather_kernel<<<grid, 256, 0, st>>>((const float4*)feat_src, (float4*)feat_dst,
+                                               upd.sgd ? nullptr : (const float4*)mom_cur, (float4*)mom_alt,
+                                               w.orig[cur], w.orig[cur ^ 1], w.idx, live_next, elems4); count_launch();
+      if (int rc = check_launch("early-exit compaction")) return rc;
+      w.act[0] = feat_dst;
+      float* t = mom_cur; mom_cur = mom_alt; mom_alt = t;
+      cur ^= 1;
+      hp.orig = w.orig[cur];
+      live = live_next;
+      hp.live = live;
     }
-    if (int rc = run_forward(c, w, Bact, cfg->math, st)) return rc;                   // :73
+    if (int rc = run_forward(c, w, B, cfg->math, st, live)) return rc;                   // :73
     hp.step = i;
     hp.dpre = (i + 1 < K) ? w.g[0] : nullptr;         // the gradient after the last step is never consumed
-    if (int rc = head_launch(c, w, Bact, hp, cfg->math, st)) return rc;                          // :76-83
+    if (int rc = head_launch(c, w, B, hp, cfg->math, st)) return rc;                          // :76-83
   }
-  if (compacting && Bact > 0) {
-    scatter_active_kernel<<<(unsigned)Bact, 128, 0, st>>>((const float4*)w.act[0], hp.orig, w.done, (float4*)feature_out,
-                                                          (int)(c.act_elems[0] / 4)); count_launch();
+  if (compacting) {
+    scatter_active_kernel<<<(unsigned)B, 128, 0, st>>>((const float4*)w.act[0], hp.orig, w.done, live, (float4*)feature_out,
+                                                       elems4); count_launch();
     if (int rc = check_launch("scatter_active_kernel")) return rc;
   }
   return CGS_OK;

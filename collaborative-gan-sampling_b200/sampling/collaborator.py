@@ -56,6 +56,9 @@ class Refiner():
         self.discriminator = discriminator
         self.feature_to_data = feature_to_data
         self.func_loss = func_loss
+        # captured graphs hold the weight / bias pointers of the previous environment by value: never replay them
+        # against another one (their cache entries also keep the specs they were captured with alive)
+        self._graphs = {}
         self._d = spec_d.d
         self._g = spec_g.gtail
         self._spec = spec_g
@@ -176,7 +179,7 @@ class Refiner():
                                         L.ptr(b["default_logit"]), L.ptr(b["idx"]), L.ptr(b["best_feat"]), L.ptr(ws),
                                         ws.numel(), L.stream_ptr()))
 
-        if not self.cuda_graph or cfg.early_exit:      # early exit re-sizes the batch on the host: no graph replay
+        if not self.cuda_graph:
             b = buffers()
             b["feat"].copy_(feat_in)                                  # tf.identity (collaborator.py:48,58)
             if idx_host is not None:
@@ -185,7 +188,7 @@ class Refiner():
         else:
             # the launch sequence depends only on (shapes, config): capture it once, replay afterwards
             key = (B, mode, cfg.steps, cfg.rate, cfg.method, cfg.alpha, cfg.clip, cfg.vmin, cfg.vmax, cfg.math,
-                   cfg.early_exit, cfg.exit_logit, keep_optimal_feature)
+                   cfg.early_exit, cfg.exit_logit, keep_optimal_feature, id(self._g), id(self._d), str(dev))
             ent = self._graphs.get(key)
             if ent is None:
                 b = buffers()
@@ -203,8 +206,8 @@ class Refiner():
                 n0 = lib.cgs_launch_count()
                 with torch.cuda.graph(graph):
                     launch(b, ws)
-                ent = self._graphs[key] = (graph, b, ws, int(lib.cgs_launch_count() - n0))
-            graph, sb, _, n_kernels = ent
+                ent = self._graphs[key] = (graph, b, ws, int(lib.cgs_launch_count() - n0), (self._g, self._d))
+            graph, sb, _, n_kernels, _ = ent
             self.replayed_launches += n_kernels
             sb["feat"].copy_(feat_in)
             if idx_host is not None:

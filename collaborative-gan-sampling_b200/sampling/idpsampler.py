@@ -96,8 +96,35 @@ class IndependenceSampler():
                            torch.tensor([self._cnt_host], dtype=torch.int32, device=dev))
         return self._state
 
+    def emit_capacity(self, n):
+        """Upper bound on the rows one call over ``n`` scores can emit (the thinning counter emits at most once per
+        ``thin_period + 1`` processed rows, idpsampler.py:34-39; +2 covers the carried counter)."""
+        return int(n) // (int(self.thin_period) + 1) + 2
+
+    def select_async(self, sigmoids, uniforms=None):
+        """``select`` without any host synchronisation: returns (emit_src [emit_capacity(n)] int32, count [1] int32),
+        both on the device; rows past ``count`` are undefined.  The score-range assertion of idpsampler.py:22-23
+        is skipped (it would need a host read); everything else is the same chain."""
+        return self._select(sigmoids, uniforms, sync=False)
+
+    def gather_async(self, samples):
+        """Rows emitted by the last ``select_async`` -> (rows [emit_capacity, ...] float32, count [1]); device only."""
+        dev = R.require_cuda()
+        smp, _ = R.to_device(samples)
+        emit, count = self.last_emit_src, self._last_count
+        src = (smp if smp.dtype == torch.float32 else smp.to(torch.float32)).contiguous()
+        cap = emit.numel()
+        out = torch.empty((cap,) + tuple(src.shape[1:]), dtype=torch.float32, device=dev)
+        if cap and src.shape[0]:
+            L.check(L.load().cgs_gather_rows(L.ptr(src), src[0].numel() * 4, L.ptr(emit), L.ptr(count), cap, L.ptr(out),
+                                             L.stream_ptr()))
+        return out, count
+
     def select(self, sigmoids, uniforms=None):
         """Run the chain over the scores only; returns the emitted source rows (device int32, ascending)."""
+        return self._select(sigmoids, uniforms, sync=True)
+
+    def _select(self, sigmoids, uniforms, sync):
         dev = R.require_cuda()
         lib = L.load()
         sig, _ = R.to_device(sigmoids)
@@ -105,7 +132,7 @@ class IndependenceSampler():
             sig = sig.to(torch.float64)
         sig = sig.reshape(sig.shape[0], -1)[:, 0].contiguous()
         n = sig.numel()
-        if n:
+        if n and sync:
             lo, hi = torch.aminmax(sig)
             assert float(lo) >= 0.0                             # idpsampler.py:22
             assert float(hi) <= 1.0                             # idpsampler.py:23
@@ -113,6 +140,13 @@ class IndependenceSampler():
         seed, offset = 0, 0
         if uniforms is not None:
             u, _ = R.to_device(uniforms, torch.float64)
+            u = u.reshape(-1)
+            if u.numel() < n:                                         # the kernel reads one uniform per processed row
+                self._pull()                                          # (host read of the state only in this rare case)
+                need = n - 1 if (self._d_host is None and n > 0) else n   # no draw for the first move without d_curr
+                if u.numel() < need:
+                    raise ValueError("uniforms has %d entries, the chain over %d rows needs %d (idpsampler.py:50)"
+                                     % (u.numel(), n, need))
         elif self.rng == "numpy":
             # one np.random.uniform(0, 1) per row (idpsampler.py:50); none for the first row when d_curr is None
             self._pull()
@@ -131,9 +165,13 @@ class IndependenceSampler():
         L.check(lib.cgs_mh_accept(L.ptr(sig), R.score_dtype(sig), n, L.ptr(u), seed, offset, L.ptr(d), L.ptr(kind),
                                   L.ptr(cnt), int(self.thin_period), int(self.burn_in), L.ptr(accepted), L.ptr(emit),
                                   L.ptr(count), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        self._last_count = count
+        if not sync:
+            cap = min(self.emit_capacity(n), emit.numel())
+            self.last_accepted, self.last_emit_src = accepted[:n], emit[:cap]
+            return self.last_emit_src, count
         k = int(count.item())
         self.last_accepted, self.last_emit_src = accepted[:n], emit[:k]
-        self._last_count = count
         return self.last_emit_src
 
     def gather(self, samples):

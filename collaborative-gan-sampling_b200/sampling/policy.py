@@ -67,6 +67,16 @@ class PolicyAdaptive(object):
             ls = ls.reshape(-1)
             if ls.numel() != rows:
                 raise ValueError("loss must have one entry per row")
+        # the state of an earlier call must fit this theta: the reference's numpy / TF arithmetic raises a broadcast
+        # error when the batch shape changes without reset_moving_average(); the kernel would index out of bounds
+        for name in ("momentum", "mean_square"):
+            st = getattr(self, name)
+            if st is not None and (tuple(st.shape) != tuple(th.shape) or st.device != th.device):
+                raise ValueError("operands could not be broadcast together with shapes %s %s (policy state `%s`; call "
+                                 "reset_moving_average() when the batch changes)" % (tuple(st.shape), tuple(th.shape), name))
+        if self.loss is not None and (self.loss.numel() != rows or self.loss.device != th.device):
+            raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,) (policy state `loss`)"
+                             % (self.loss.numel(), rows))
         if self.method != "sgd" and first:
             self.momentum = torch.empty_like(th)
         if self.method == "ladam" and first:

@@ -66,8 +66,13 @@ class Rejector(object):
         n = sig.numel()
         u = None
         seed, offset = 0, 0
+        if n >= 2 ** 31 - 2:
+            raise ValueError("n too large for 32-bit row indices; split the batch")
         if uniforms is not None:
             u, _ = R.to_device(uniforms, torch.float64)
+            u = u.reshape(-1)
+            if u.numel() < n:                                         # the kernel reads uniforms[i] for every row
+                raise ValueError("uniforms has %d entries, %d rows need one each (rejector.py:33)" % (u.numel(), n))
         elif self.rng == "numpy":
             u, _ = R.to_device(np.random.rand(n), torch.float64)      # rejector.py:33
         elif self.rng == "philox":

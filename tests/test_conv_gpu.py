@@ -132,17 +132,20 @@ def test_build_refiner_matches_oracle(cgs_lib, cuda_device, arch_name, B, K, met
     ref = Refiner(K, 0.1, method)
     ref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
     out = ref.build_refiner(h0.to(cuda_device), None, "deterministic", keep_optimal_feature=True)
-    tol = 1e-4 if math == "fp32" else 5e-2
+    tol = 1e-4 if math == "fp32" else 1e-2          # K-step images rel-L2 <= 1e-2 in TF32 mode
     e_img = rel_l2(out.cpu().numpy(), o["refined"].numpy())
     e_logit = np.abs(ref.optimal_logit.cpu().numpy() - o["optimal_logit"].numpy()).max()
     e_feat = rel_l2(ref.current_feature.cpu().numpy(), o["final_feature"].numpy())
     print(arch_name, math, "default", o["default_logit"].numpy(), "optimal", o["optimal_logit"].numpy(), "steps",
           o["optimal_step"].numpy(), "| img rel %.2e logit abs %.2e final feature rel %.2e" % (e_img, e_logit, e_feat))
+    ltol = tol if math == "fp32" else 2e-2          # logits within 2 % (of max(1, |logit|)) in TF32 mode
     assert e_img <= tol and e_feat <= tol
-    assert e_logit <= tol * max(1.0, np.abs(o["optimal_logit"].numpy()).max())
-    assert np.abs(ref.default_logit.cpu().numpy() - o["default_logit"].numpy()).max() <= tol * 2
+    assert e_logit <= ltol * max(1.0, np.abs(o["optimal_logit"].numpy()).max())
+    assert np.abs(ref.default_logit.cpu().numpy() - o["default_logit"].numpy()).max() <= ltol * 2
     if math == "fp32":
         assert np.array_equal(ref.optimal_step.cpu().numpy(), o["optimal_step"].numpy())
+    else:
+        assert (ref.optimal_step.cpu().numpy() == o["optimal_step"].numpy()).mean() >= 0.5   # ties between near-equal steps
     assert rel_l2(ref.optimal_feature.cpu().numpy(), o["optimal_feature"].numpy()) <= tol
 
 
@@ -274,6 +277,16 @@ def test_early_exit_compaction_matches_oracle(cgs_lib, cuda_device, arch_name, B
     if bool(stay.any()):
         assert torch.equal(ee_img[stay], a[stay]) and torch.equal(ee_logit[stay], plain.optimal_logit[stay])
         assert torch.equal(ee_feat[stay], plain.current_feature[stay])
+    # the device-side compaction has no host synchronisation: the whole K loop is CUDA-graph capturable and the
+    # replay gives the same bits as the eager launches, call after call
+    gref = Refiner(K, 0.1, cuda_graph=True)
+    gref.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    gref.early_exit_logit = thr
+    for _ in range(2):
+        gout = gref.build_refiner(h0.to(cuda_device), keep_optimal_feature=True)
+        assert torch.equal(gout, ee_img) and torch.equal(gref.optimal_logit, ee_logit)
+        assert torch.equal(gref.current_feature, ee_feat) and torch.equal(gref.optimal_step, ref.optimal_step)
+        assert torch.equal(gref.optimal_feature, ref.optimal_feature)
     ref.early_exit_logit = 1e30
     b = ref.build_refiner(h0.to(cuda_device))
     assert torch.equal(a, b) and torch.equal(plain.optimal_logit, ref.optimal_logit)

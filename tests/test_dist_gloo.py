@@ -35,6 +35,20 @@ def _worker(rank, world, port, n_global, ragged, ret):
     emit, _, _, _ = snp.mh_chain(g.numpy().reshape(-1, 1), u, np.float32(0.4), 1, 3, 0)
     acc = D.gather_accepted(local_rows, torch.from_numpy(emit), bounds)
     assert torch.equal(acc, torch.from_numpy(rows[emit]))
+    # device-resident variant (no host read-backs): padded emit list + count, one int32 all-reduce merges the rows
+    rows_nz = rows.copy()
+    rows_nz[::7, 1] = -0.0                                        # sign bit of a negative zero must survive the merge
+    cap = len(emit) + 5
+    emit_pad = torch.zeros(cap, dtype=torch.int32)
+    emit_pad[:len(emit)] = torch.from_numpy(emit).int()
+    emit_pad[len(emit):] = 12345678                               # garbage past the count must be ignored
+    cnt = torch.tensor([len(emit)], dtype=torch.int32)
+    acc2, cnt2 = D.gather_accepted_async(torch.from_numpy(rows_nz[lo:hi]), emit_pad, cnt, lo, hi)
+    assert int(cnt2) == len(emit) and acc2.shape[0] == cap
+    assert np.array_equal(acc2[:len(emit)].numpy().view(np.int32), rows_nz[emit].view(np.int32))
+    assert not acc2[len(emit):].any()
+    st = D.reduce_stats_async(torch.tensor(hi - lo), local_scores.double().sum(), local_scores.max())
+    assert float(st[0]) == n_global and float(st[2]) == float(scores.max())
     n, ssum, smax = D.reduce_stats(hi - lo, float(local_scores.double().sum()), float(local_scores.max()))
     assert n == n_global and abs(ssum - float(scores.astype(np.float64).sum())) < 1e-9 and smax == float(scores.max())
     if rank == 0:

@@ -26,6 +26,59 @@ def test_proposal_head_matches_oracle(cgs_lib, cuda_device, name, math, tol):
     assert got.shape == ref.shape and rel <= tol
 
 
+def _stream(seed, dim=3):
+    rng = np.random.RandomState(seed)
+
+    def propose(n):
+        return rng.randn(n, dim).astype(np.float32), rng.beta(2, 5, size=(n, 1)).astype(np.float32)
+    return propose
+
+
+@pytest.mark.parametrize("kind,T,eval_size,batch", [("rejection", 0, 300, 64), ("hastings", 3, 300, 64),
+                                                    ("hastings", 20, 128, 32), ("synthetic", 5, 257, 0)])
+def test_fill_up_matches_oracle_loop(cgs_lib, cuda_device, kind, T, eval_size, batch):
+    """cgs.fillup vs the oracle restatement of nsgan/GAN.py:311-433 / synthetic/main.py:149-214 under the SAME proposals
+    and the SAME uniforms (both sides draw from the global numpy RNG exactly like the reference): accepted rows in
+    order, cnt, cnt_propose, back-fill count."""
+    from cgs import fillup as P
+    from oracle import fillup_np as F
+    from sampling.idpsampler import IndependenceSampler
+    from sampling.rejector import Rejector
+    res = {}
+    for side in ("oracle", "product"):
+        propose = _stream(3)
+        base_x, base_s = propose(eval_size)
+        np.random.seed(11)
+        if kind == "rejection":
+            smp = F.OracleRejector() if side == "oracle" else Rejector()
+            smp.set_score_max(np.float32(0.9))
+            sampling = lambda x, s, smp=smp: smp.sampling(x, s, shift_percent=100.0)
+            guard = "running"
+        else:
+            smp = F.OracleIndependenceSampler(T=T) if side == "oracle" else IndependenceSampler(T=T)
+            smp.set_score_curr(np.float32(0.3))
+            sampling = smp.sampling
+            guard = "batch"
+        if side == "oracle":
+            r = F.fill_up_synthetic(base_x, base_s, propose, sampling) if kind == "synthetic" else \
+                F.fill_up_nsgan(base_x, base_s, propose, sampling, eval_size, batch, store_guard=guard)
+            res[side] = (r["samples"].astype(np.float32), r["cnt"], r["cnt_propose"], r["n_backfilled"], r["n_batches"])
+        else:
+            def propose_dev(n):
+                x, sc = propose(n)
+                return torch.from_numpy(x).to(cuda_device), torch.from_numpy(sc).to(cuda_device)
+            bx, bs = torch.from_numpy(base_x).to(cuda_device), torch.from_numpy(base_s).to(cuda_device)
+            r = P.fill_up_synthetic(bx, bs, propose_dev, sampling) if kind == "synthetic" else \
+                P.fill_up(bx, bs, propose_dev, sampling, eval_size, batch, store_guard=guard)
+            assert r.samples.is_cuda
+            res[side] = (r.samples.cpu().numpy(), r.cnt, r.cnt_propose, r.n_backfilled, r.n_batches)
+    o, g = res["oracle"], res["product"]
+    assert o[1:] == g[1:], (o[1:], g[1:])
+    assert np.array_equal(o[0], g[0])
+    if kind == "hastings" and T == 20:
+        assert g[3] > 0                       # efficiency <= 1/21 < MIN_EFFICIENCY: un-filtered back-fill (App. C8)
+
+
 def test_fill_up_driver(cgs_lib, cuda_device):
     """z -> head -> refine -> MH accept, filled up to eval_size like nsgan/GAN.py:384-433, all on the device."""
     from cgs import nets as N, synthetic as S
@@ -41,21 +94,16 @@ def test_fill_up_driver(cgs_lib, cuda_device):
     g = torch.Generator(device="cpu").manual_seed(0)
 
     def propose(n):
-        return head(torch.rand(n, arch["z_dim"], generator=g) * 2 - 1)
-
-    def refine(h):
-        return refiner.build_refiner(h)
-
-    def score(x):
-        return torch.sigmoid(refiner.optimal_logit)
+        x = refiner.build_refiner(head(torch.rand(n, arch["z_dim"], generator=g) * 2 - 1))
+        return x, torch.sigmoid(refiner.optimal_logit)
 
     mh = IndependenceSampler(T=3, rng="philox", seed=1)
     mh.set_score_curr(np.float32(0.5))
-    out, eff, backfilled = fill_up(propose, score, mh, eval_size=96, batch_size=32, refine=refine)
-    assert out.shape == (96, 28, 28, 1) and out.is_cuda and torch.isfinite(out).all()
-    assert 0.0 < eff <= 0.25 + 1e-6          # T=3 -> at most one emission per 4 proposals
+    r = fill_up(*propose(96), propose, mh.sampling, eval_size=96, batch_size=32)
+    assert r.samples.shape == (96, 28, 28, 1) and r.samples.is_cuda and torch.isfinite(r.samples).all()
+    assert 0.0 < r.efficiency <= 0.25 + 0.05       # T=3 -> about one emission per 4 proposals (+ back-filled rows)
     # with T=20 efficiency < MIN_EFFICIENCY: the driver back-fills un-filtered batches like the reference (App. C8)
     mh2 = IndependenceSampler(T=20, rng="philox", seed=1)
     mh2.set_score_curr(np.float32(0.5))
-    out2, eff2, backfilled2 = fill_up(propose, score, mh2, eval_size=64, batch_size=32, refine=refine)
-    assert out2.shape[0] == 64 and backfilled2 > 0
+    r2 = fill_up(*propose(64), propose, mh2.sampling, eval_size=64, batch_size=32)
+    assert r2.samples.shape[0] == 64 and r2.n_backfilled > 0
