@@ -39,6 +39,7 @@ class Refiner():
         self.math = math
         self.early_exit_logit = None      # opt-in (README.md:13); None = reference behaviour (best of K)
         self.cuda_graph = cuda_graph      # capture the K-step launch sequence once per batch shape and replay it
+        self.chunk_rows = None            # refine at most this many rows per launch sequence (bounds the workspace)
         self._graphs = {}
         self.replayed_launches = 0        # kernels executed through graph replays (cgs_launch_count sees captures only)
         self._ws = R.Workspace()
@@ -132,6 +133,8 @@ class Refiner():
         # the kernels index rows with 32 bits: very large batches are refined in independent chunks (samples are
         # independent under inference-mode BN, so chunking does not change a single bit)
         limit = self._max_rows_per_launch()
+        if self.chunk_rows:
+            limit = max(1, min(limit, int(self.chunk_rows)))
         if B > limit:
             if prob_indices is None and mode == 'probabilistic':
                 prob_indices = np.random.randint(self.forward_steps + 1, size=B)
