@@ -411,6 +411,13 @@ __host__ __device__ constexpr bool n2_need(int nt, int dyi) {       // does clas
   return (nt + 3 - 2 * dyi) >= 0 && (nt + 3 - 2 * dyi) < KS;         // ky = py + pad - 2 dy, pad = 1
 }
 
+// Four 8x4 TF32 sub-matrices (8 rows of 16 bytes each) -> the A fragment of mma.m16n8k8 in register order: lanes 0-7
+// address the rows of (pixels g, k 0-3), lanes 8-15 (pixels g+8, k 0-3), lanes 16-23 (g, k 4-7), lanes 24-31 (g+8, k 4-7).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
 __device__ __forceinline__ void n2_setup(const EdgeNarrowParams& p, float2* bfrag) {
   for (int idx = threadIdx.x; idx < N2_BFRAG; idx += blockDim.x) {
     const int l = idx & 31, nt = (idx >> 5) & 1, ks = (idx >> 6) & 7, sh = idx >> 9;
@@ -418,10 +425,11 @@ __device__ __forceinline__ void n2_setup(const EdgeNarrowParams& p, float2* bfra
     const int g = l >> 2, t = l & 3;
     const int py = nt, px = g >> 2, c = g & 3;
     const int ky = py + p.pad_y - 2 * dy, kx = px + p.pad_x - 2 * dx;
-    const int ch = 16 * (ks >> 1) + 4 * t + 2 * (ks & 1);            // same K permutation as narrow_mma
-    float2 b = make_float2(0.f, 0.f);
-    if (c < p.cimg && ky >= 0 && ky < p.k && kx >= 0 && kx < p.k)
-      b = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)((ky * p.k + kx) * 4 + c) * p.K + ch));
+    float2 b = make_float2(0.f, 0.f);                                // b0 = W[k = t][n = g], b1 = W[k = t + 4][n = g]
+    if (c < p.cimg && ky >= 0 && ky < p.k && kx >= 0 && kx < p.k) {
+      const float* wr = p.w + (size_t)((ky * p.k + kx) * 4 + c) * p.K + 8 * ks + t;
+      b = make_float2(__ldg(wr), __ldg(wr + 4));
+    }
     bfrag[idx] = b;
   }
 }
@@ -445,12 +453,16 @@ __global__ void __launch_bounds__(256, 1) edge_narrow2_kernel(const EdgeNarrowPa
   const float bias0 = (t & 1) ? bias4.z : bias4.x, bias1 = (t & 1) ? bias4.w : bias4.y;
   const int c0 = (t & 1) * 2;                       // image channels this lane holds: c0, c0 + 1
   const bool bwd = p.e.epi == EPI_BWD;
+  // ldmatrix row address of this lane: stored pixel (lane & 7) + 8 * bit 3 (+ 16 m + dx), 16-byte chunk 2 ks + bit 4
+  const int lm_px = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int lm_half = lane >> 4;
 
   for (int job = blockIdx.x * nwarps + warp; job < njobs; job += gridDim.x * nwarps) {
     const int b = job / p.bands;
     const int j0 = (job - b * p.bands) * p.R;
     const int j1 = min(p.IH, j0 + p.R);              // output-row pairs [j0, j1)
     const float* src_img = p.in + (size_t)b * p.IH * p.IW * 64;
+    // three accumulator sets: output-row pairs j = r + 1, r, r - 1 of the input row r being swept
     float acc[3][MT][2][4];
 #pragma unroll
     for (int s3 = 0; s3 < 3; ++s3)
@@ -461,21 +473,22 @@ __global__ void __launch_bounds__(256, 1) edge_narrow2_kernel(const EdgeNarrowPa
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[s3][m][nt][q] = 0.f;
 
-    // stage input row r into buffer `buf` (16-byte chunk c of pixel x lands at chunk c ^ 4 * (stored pixel & 1))
+    // stage input row r into buffer `buf`: 16-byte chunk c of stored pixel x lands at chunk (c & 8) | ((c ^ x) & 7), so
+    // that the eight 16-byte rows of an ldmatrix sub-matrix (8 consecutive pixels, same chunk) hit distinct banks
     auto stage_row = [&](int r, int buf) {
       if ((unsigned)r < (unsigned)p.IH) {
         const float* src = src_img + (size_t)r * p.IW * 64;
         const uint32_t dst = rowbuf_u32 + buf * (N2_ROW_FLOATS * 4);
         for (int q = lane; q < p.IW * 16; q += 32) {
           const int px = (q >> 4) + 1, ck = q & 15;
-          cp_async_16(dst + px * 256 + ((ck ^ ((px & 1) << 2)) << 4), src + q * 4, 16u);
+          cp_async_16(dst + px * 256 + (((ck & 8) | ((ck ^ px) & 7)) << 4), src + q * 4, 16u);
         }
       }
       cp_async_commit();
     };
 
-    // epilogue of the output-row pair j held in accumulator set `st`
-    auto finalize = [&](int j, float (&a)[MT][2][4], const float2 (&aux)[MT][2][2]) {
+    // epilogue of the output-row pair j held in accumulator set `a` (stale sets are zeroed, never stored)
+    auto finalize = [&](int j, bool store, float (&a)[MT][2][4], const float2 (&aux)[MT][2][2]) {
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         float* orow = p.out + ((size_t)b * p.OH + 2 * j + nt) * p.out_pitch * 4;
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(256, 1) edge_narrow2_kernel(const EdgeNarrowPa
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int i = 16 * m + 8 * h + g;
-            if (i < p.IW) {
+            if (store && i < p.IW) {
               const float x0a = bwd ? aux[m][nt][h].x : bias0, x0b = bwd ? aux[m][nt][h].y : bias1;
               float unused;
               float2 o;
@@ -497,14 +510,18 @@ __global__ void __launch_bounds__(256, 1) edge_narrow2_kernel(const EdgeNarrowPa
           }
         // margins of the pitched layout are zeros
         const int nmargin = p.out_pitch - p.OW;
-        if (lane < nmargin) {
+        if (store && lane < nmargin) {
           const int col = lane < p.out_xoff ? lane : p.OW + lane;
           *reinterpret_cast<float4*>(orow + (size_t)col * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
 
-    // one input row: PH = (r - (j0 - 1)) % 3 selects which register set belongs to which output-row pair
+    // one input row: PH = (r - (j0 - 1)) % 3 selects which register set belongs to which output-row pair.  All three
+    // targets are always accumulated (no branches around the MMAs: 10 independent accumulators per k-step hide the
+    // mma.sync latency with only two warps per scheduler); the set of a pair outside the band collects garbage and is
+    // zeroed, never stored, when its turn to be finalised comes.  The k-step loop is deliberately NOT fully unrolled:
+    // the fully unrolled kernel was 140 KB of code and spent 20 % of its issue slots on instruction-cache misses.
     auto row_step = [&](int r, int buf, auto ph_tag) {
       constexpr int PH = decltype(ph_tag)::value;
       cp_async_wait<0>();
@@ -529,44 +546,35 @@ __global__ void __launch_bounds__(256, 1) edge_narrow2_kernel(const EdgeNarrowPa
         }
       }
       if ((unsigned)r < (unsigned)p.IH) {
-        const float* rb = rowbuf + buf * N2_ROW_FLOATS;
-        // which of the three targets exist for this row (band edges): j = r + 1 (dy = -1), r (dy = 0), r - 1 (dy = +1)
-        const bool ok0 = r + 1 >= j0 && r + 1 < j1, ok1 = r >= j0 && r < j1, ok2 = r - 1 >= j0 && r - 1 < j1;
+        const uint32_t rb = rowbuf_u32 + buf * (N2_ROW_FLOATS * 4);
+        constexpr int kSetOf[3] = {(PH + 1) % 3, PH, (PH + 2) % 3};    // dy = -1, 0, +1  ->  pair j = r + 1, r, r - 1
 #pragma unroll
         for (int dxi = 0; dxi < 3; ++dxi) {
+          const int swz = (lm_px + dxi) & 7;                            // low bits of the stored pixel index
+          const uint32_t abase = rb + (uint32_t)(lm_px + dxi) * 256u;
+          const float2* bsh = bfrag + (size_t)dxi * (EN_KSTEPS * 2 * 32) + lane;   // shift (dy, dx) at + dyi * 3 * 512
+#pragma unroll 2
+          for (int ks = 0; ks < EN_KSTEPS; ++ks) {
+            const int ck = 2 * ks + lm_half;
+            const uint32_t coff = (uint32_t)(((ck & 8) | ((ck ^ swz) & 7)) << 4);
+            uint32_t af[MT][4];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            float4 va[MT], vb[MT];
+            for (int m = 0; m < MT; ++m) ldmatrix_x4(af[m], abase + (uint32_t)m * (16u * 256u) + coff);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              const int pa = 16 * m + g + dxi, pb = pa + 8;            // stored pixel = i + 1 + dx
-              va[m] = *reinterpret_cast<const float4*>(rb + pa * 64 + (((4 * j4 + t) ^ ((pa & 1) << 2)) << 2));
-              vb[m] = *reinterpret_cast<const float4*>(rb + pb * 64 + (((4 * j4 + t) ^ ((pb & 1) << 2)) << 2));
-            }
-#pragma unroll
-            for (int dyi = 0; dyi < 3; ++dyi) {
-              constexpr int kSetOf[3] = {(PH + 1) % 3, PH, (PH + 2) % 3};
-              const bool ok = dyi == 0 ? ok0 : (dyi == 1 ? ok1 : ok2);
-              if (!ok) continue;                                        // warp-uniform
+            for (int dyi = 0; dyi < 3; ++dyi)
 #pragma unroll
               for (int nt = 0; nt < 2; ++nt) {
                 if (!n2_need<KS>(nt, dyi)) continue;                    // compile time
-                const int sh = dyi * 3 + dxi;
-                const float2 be = bfrag[((sh * EN_KSTEPS + 2 * j4) * 2 + nt) * 32 + lane];
-                const float2 bo = bfrag[((sh * EN_KSTEPS + 2 * j4 + 1) * 2 + nt) * 32 + lane];
+                const float2 bq = bsh[(size_t)dyi * (3 * EN_KSTEPS * 2 * 32) + (ks * 2 + nt) * 32];
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                  mma_tf32(acc[kSetOf[dyi]][m][nt], __float_as_uint(va[m].x), __float_as_uint(vb[m].x),
-                           __float_as_uint(va[m].y), __float_as_uint(vb[m].y), __float_as_uint(be.x), __float_as_uint(be.y));
-                  mma_tf32(acc[kSetOf[dyi]][m][nt], __float_as_uint(va[m].z), __float_as_uint(vb[m].z),
-                           __float_as_uint(va[m].w), __float_as_uint(vb[m].w), __float_as_uint(bo.x), __float_as_uint(bo.y));
-                }
+                for (int m = 0; m < MT; ++m)
+                  mma_tf32(acc[kSetOf[dyi]][m][nt], af[m][0], af[m][1], af[m][2], af[m][3], __float_as_uint(bq.x),
+                           __float_as_uint(bq.y));
               }
-            }
           }
         }
       }
-      if (fin) finalize(jf, acc[(PH + 2) % 3], aux);
+      finalize(jf, fin, acc[(PH + 2) % 3], aux);      // store if the pair is in the band; zero the set either way
     };
 
     __syncwarp();                                     // previous job's reads of the row buffers are done
