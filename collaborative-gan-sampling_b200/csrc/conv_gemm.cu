@@ -58,30 +58,35 @@ constexpr int EPI_PITCH = 20;                // floats per staged row (16-byte a
 constexpr int kMaxEpiWarps = kEpiWarps + kProdWarps;              // producer warps help in TMA mode
 constexpr int EPI_STAGE_BYTES = kMaxEpiWarps * 32 * EPI_PITCH * 4;   // 30 KB
 
-template <int BN>
+template <int BN, int NS = 1>
 struct Cfg {
   // K blocks ("atoms" of 32 floats) per pipeline stage: the per-stage barrier handshakes of the single-thread TMA and
-  // MMA roles cost ~400 cycles, so narrow tiles (short MMAs) take two atoms per stage to amortise them
-  static constexpr int KB = (BN >= 256) ? 1 : 2;
+  // MMA roles cost ~400 cycles, so narrow tiles (short MMAs) take two atoms per stage to amortise them.  A class-fused
+  // stage (NS > 1 accumulator slots per tile) is one A atom plus one weight atom per slot.
+  static constexpr int KB = (NS > 1 || BN >= 256) ? 1 : 2;
   static constexpr int B_ATOM_BYTES = BN * BK * 4;
   static constexpr int A_STAGE_BYTES = KB * A_ATOM_BYTES;
-  static constexpr int B_STAGE_BYTES = KB * B_ATOM_BYTES;
+  static constexpr int B_STAGE_BYTES = (NS > 1 ? NS : KB) * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-  // accumulator ring in TMEM: 4 buffers up to BN = 128 (512 columns), 2 for BN = 256
-  static constexpr int NACC = (BN >= 256) ? 2 : 4;
-  static constexpr int TMEM_COLS = NACC * BN;
+  // accumulator ring in TMEM: 4 buffers up to BN = 128 (512 columns), 2 for BN = 256; fused tiles take NS * BN
+  // columns per buffer (two buffers)
+  static constexpr int ACC_COLS = NS * BN;
+  static constexpr int NACC = NS > 1 ? 512 / ACC_COLS : ((BN >= 256) ? 2 : 4);
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;
+  static_assert(NS == 1 || (ACC_COLS <= 256 && BN <= 128), "fused tiles need two TMEM buffers");
   // up to BN = 128 each epilogue warp group owns whole tiles (three tile epilogues in flight per CTA, the per-tile
   // set-up paid by 4 warps instead of 12); at BN = 256 the groups split the 16 chunks of one tile
   static constexpr bool SPLIT_TILES = (BN <= 128);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NS>;
+  constexpr bool FUSED = NS > 1;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,7 +113,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     for (int a = 0; a < C::NACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       // one arrive per epilogue warp that reads the buffer: the 4 warps of one group, or all groups at BN = 256
-      mbar_init(&tmem_empty_bar[a], (p.a_tma && !C::SPLIT_TILES) ? kMaxEpiWarps : kEpiWarps);
+      // (fused tiles: two TMEM buffers but three epilogue groups -- whole-tile ownership would let a group run two
+      //  buffer uses ahead and alias the barrier parity, so the groups share every tile's chunks instead)
+      mbar_init(&tmem_empty_bar[a], (p.a_tma && (!C::SPLIT_TILES || FUSED)) ? kMaxEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -232,6 +239,27 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const int ci = fast_div(tile, fd_tpc);
         const int rem = tile - ci * tiles_per_class;
         const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
+        if (FUSED) {
+          // ci = class group: per (shift, channel block) one weight atom per class that has a tap at the shift
+          const FuseGroup& G = p.grp[ci];
+          for (int si = 0; si < G.nshifts; ++si) {
+            const FuseShift& sh = p.shf[G.shift0 + si];
+            for (int cb = 0; cb < p.cblocks; ++cb, ++it_global) {
+              const uint32_t s = stage, ph = phase;
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              if (skip) {
+                mbar_arrive(&full_bar[s]);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)sh.ncls * C::B_ATOM_BYTES);
+                for (int q = 0; q < sh.ncls; ++q)
+                  tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES + sh.slot[q] * C::B_ATOM_BYTES, &tmap_w, &full_bar[s], 0,
+                              n_tile * BN, sh.katom0[q] + cb);
+              }
+            }
+          }
+          continue;
+        }
         const int katom0 = p.cls[ci].k0 / BK;
         const int nkb = p.cls[ci].nkb;
         for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
@@ -261,11 +289,29 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           const int ci = fast_div(tile, fd_tpc);
           const int rem = tile - ci * tiles_per_class;
           const int m_tile = fast_div(rem, p.fd_n_tiles);
-          const GemmClass& gc = p.cls[ci];
-          const int nkb = gc.nkb;
           const int mb = fast_div(m_tile, p.fd_hy_tiles);
           const int b0 = mb * p.BB;
           const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
+          if (FUSED) {
+            const FuseGroup& G = p.grp[ci];
+            for (int si = 0; si < G.nshifts; ++si) {
+              const FuseShift& sh = p.shf[G.shift0 + si];
+              for (int cb = 0; cb < cblocks; ++cb) {
+                const uint32_t s = stage, ph = phase;
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (skip) {
+                  mbar_arrive(&full_bar[s]);
+                } else {
+                  mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+                  tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, sh.dx, y_tile + sh.dy, b0);
+                }
+              }
+            }
+            continue;
+          }
+          const GemmClass& gc = p.cls[ci];
+          const int nkb = gc.nkb;
           const int cb0 = gc.cb0;
           int t = 0, cb = 0;
           for (int kb = 0; kb < nkb; kb += C::KB) {
@@ -312,11 +358,41 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const bool skip_mma = (p.debug & 4) != 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
       const int ci = fast_div(tile, fd_tpc);
-      const int nkb = p.cls[ci].nkb;
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
-      const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
+      if (FUSED) {
+        const FuseGroup& G = p.grp[ci];
+        uint32_t touched = 0;                    // slots that already hold a partial sum in this tile
+        for (int si = 0; si < G.nshifts; ++si) {
+          const FuseShift& sh = p.shf[G.shift0 + si];
+          for (int cb = 0; cb < p.cblocks; ++cb, ++it_global) {
+            const uint32_t s = stage;
+            const bool last = (si == G.nshifts - 1) && (cb == p.cblocks - 1);
+            mbar_wait(&full_bar[s], phase);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            tcgen05_fence_after();
+            const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
+            if (!skip_mma) {
+              for (int q = 0; q < sh.ncls; ++q) {
+                const uint32_t slot = sh.slot[q];
+                const uint32_t had = (touched >> slot) & 1u;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k)
+                  umma_tf32_ss(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
+                               (had || k > 0) ? 1u : 0u);
+                touched |= 1u << slot;
+              }
+            }
+            umma_commit(&empty_bar[s]);
+            if (last) umma_commit(&tmem_full_bar[acc]);
+          }
+        }
+        continue;
+      }
+      const int nkb = p.cls[ci].nkb;
       for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
         const uint32_t s = stage;
         const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;
@@ -359,9 +435,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const int quarter = warp & 3;
     const int group = warp >> 2;                   // 0..2
     const int ngroups = p.a_tma ? kMaxEpiWarps / 4 : 1;
-    const int tile_groups = C::SPLIT_TILES ? ngroups : 1;    // groups that take separate tiles
-    const int chunk_groups = C::SPLIT_TILES ? 1 : ngroups;   // groups that share the chunks of one tile
-    const int chunk_first = C::SPLIT_TILES ? 0 : group;
+    constexpr bool kSplitTiles = C::SPLIT_TILES && !FUSED;
+    const int tile_groups = kSplitTiles ? ngroups : 1;       // groups that take separate tiles
+    const int chunk_groups = kSplitTiles ? 1 : ngroups;      // groups that share the chunks of one tile
     float* stage = smem_epi + warp * 32 * EPI_PITCH;
     const bool dbg_skip_epi = (p.debug & 16) != 0, dbg_skip_store = (p.debug & 1024) != 0, dbg_no_prefetch = (p.debug & 2048) != 0;
     const int c4 = lane % Q;
@@ -381,7 +457,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       l_off[ps] = ((bb * p.OH + hh * p.os) * p.OW + i * p.os) * p.ON;
       l_pos[ps] = r < p.rows_valid ? (multi_img ? bb : hh) : (1 << 28);   // padding rows never pass the bound test
     }
-    for (uint32_t tile_count = C::SPLIT_TILES ? group : 0;; tile_count += tile_groups) {
+    for (uint32_t tile_count = kSplitTiles ? group : 0;; tile_count += tile_groups) {
       const int tile = blockIdx.x + tile_count * gridDim.x;
       if (tile >= total_tiles) break;
       const int ci = fast_div(tile, fd_tpc);
@@ -393,7 +469,16 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const int j0 = (m_tile - mb * p.hy_tiles) * p.BH;
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
-      const int t_off = ((b0 * p.OH + j0 * p.os + p.cls[ci].oy0) * p.OW + p.cls[ci].ox0) * p.ON;
+      // a fused tile holds one accumulator per class of its group (slots): the same epilogue runs once per slot with
+      // that class's output offsets; the TMEM buffer goes back to the MMA warp after the last slot has been read
+      const int nslots = FUSED ? p.grp[ci].ncls : 1;
+      bool waited = false;
+      for (int slot = 0; slot < nslots; ++slot) {
+      const int cls_i = FUSED ? p.grp[ci].cls[slot] : ci;
+      const bool last_slot = slot == nslots - 1;
+      // first chunk of this warp's group (rotated per slot so the three groups get equal shares of a fused tile)
+      const int chunk_first = kSplitTiles ? 0 : (FUSED ? (group + slot) % ngroups : group);
+      const int t_off = ((b0 * p.OH + j0 * p.os + p.cls[cls_i].oy0) * p.OW + p.cls[cls_i].ox0) * p.ON;
       int ro[PASSES];                              // element offset of each stored row in out / aux / mom, -1 = none
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps)
@@ -423,10 +508,13 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         }
       };
       prefetch(chunk_first);                       // in flight while the main loop of this tile still runs
-      mbar_wait(&tmem_full_bar[acc], acc_ph);
-      if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (!waited) {
+        mbar_wait(&tmem_full_bar[acc], acc_ph);
+        if (warp == 0 && lane == 0) trace(p, 3, 0, tile_count);
+        tcgen05_fence_after();
+        waited = true;
+      }
+      const uint32_t taddr = tmem_base + acc * C::ACC_COLS + (FUSED ? slot * BN : 0) + (static_cast<uint32_t>(quarter * 32) << 16);
       bool released = false;
 #pragma unroll 1
       for (int ch0 = chunk_first; ch0 < nch || !released; ch0 += chunk_groups * MAXOWN) {
@@ -439,10 +527,12 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         tmem_ld_wait();
         if (warp == 0 && lane == 0) trace(p, 4, 0, tile_count * 8 + ch0);
         if (ch0 + chunk_groups * MAXOWN >= nch) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
+          if (last_slot) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
+          }
           released = true;
         }
 #pragma unroll
@@ -477,6 +567,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           if (warp == 0 && lane == 0) trace(p, 4, 3, tile_count * 8 + ch);
         }
       }
+      }  // slots
       if (warp == 0 && lane == 0) trace(p, 3, 2, tile_count);
     }
   }
@@ -602,9 +693,69 @@ int pick_bn_for(const ConvGemmParams& p, int num_sms) {
   return bn;
 }
 
-template <int BN, int EPI>
+// Class-fusion tables of a transposed-type pass (see FuseShift): NS slots per tile; NS == 4 puts all four parity
+// classes into one group, NS == 2 makes one group per output-row parity (heavier group first).
+void build_fusion(ConvGemmParams& p, int NS) {
+  const int C = p.cblocks * BK;
+  p.fuse = NS;
+  p.ngroups = 0;
+  int nshf = 0;
+  int order[2] = {0, 1};
+  if (NS == 2) {                                  // groups by oy0; the one with more taps first
+    int taps[2] = {0, 0};
+    for (int c = 0; c < p.nclasses; ++c) taps[p.cls[c].oy0 & 1] += p.cls[c].ntaps;
+    if (taps[1] > taps[0]) { order[0] = 1; order[1] = 0; }
+  }
+  const int ngroups = NS == 2 ? 2 : 1;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    FuseGroup& G = p.grp[p.ngroups++];
+    G.ncls = 0;
+    for (int c = 0; c < p.nclasses; ++c)
+      if (NS != 2 || (p.cls[c].oy0 & 1) == order[gi]) G.cls[G.ncls++] = c;
+    G.shift0 = nshf;
+    for (int dy = 1; dy >= -1; --dy)
+      for (int dx = 1; dx >= -1; --dx) {
+        FuseShift sh;
+        std::memset(&sh, 0, sizeof(sh));
+        sh.dy = (signed char)dy;
+        sh.dx = (signed char)dx;
+        for (int q = 0; q < G.ncls; ++q) {
+          const GemmClass& gc = p.cls[G.cls[q]];
+          for (int t = 0; t < gc.ntaps; ++t)
+            if (gc.dy[t] == dy && gc.dx[t] == dx) {
+              sh.slot[sh.ncls] = (unsigned char)q;
+              sh.katom0[sh.ncls] = (gc.k0 + t * C) / BK;
+              ++sh.ncls;
+            }
+        }
+        if (sh.ncls) p.shf[nshf++] = sh;
+      }
+    G.nshifts = nshf - G.shift0;
+  }
+}
+
+// Can this launch run class-fused, and with how many slots per tile?  (CGS_DEBUG bit 524288 switches fusion off.)
+int fusion_slots(const ConvGemmParams& p, int bn) {
+  if (debug_flags() & (524288 | 512)) return 0;
+  if (p.nclasses != 4 || p.S != 1 || p.os != 2 || p.cblocks <= 0 || p.window || bn != p.N) return 0;
+  for (int c = 0; c < 4; ++c) {
+    if (p.cls[c].cb0 != 0 || p.cls[c].k0 % BK) return 0;
+    for (int t = 0; t < p.cls[c].ntaps; ++t)
+      if (p.cls[c].dy[t] < -1 || p.cls[c].dy[t] > 1 || p.cls[c].dx[t] < -1 || p.cls[c].dx[t] > 1) return 0;
+  }
+  // a fused stage carries one weight atom per class with a tap at its shift: k = 5 averages 25 / 9 = 2.8 classes per
+  // stage, k = 4 only 16 / 9 = 1.8 -- too little MMA work per pipeline hand-shake (measured slower on the MNIST nets)
+  int taps = 0;
+  for (int c = 0; c < 4; ++c) taps += p.cls[c].ntaps;
+  if (taps < 23) return 0;
+  if (bn == 128) return 2;
+  if (bn == 64 || bn == 32) return 4;
+  return 0;
+}
+
+template <int BN, int EPI, int NS = 1>
 int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NS>;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
@@ -666,30 +817,31 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
   const int num_sms = device_num_sms();
   {
     static DynSmemCache smem_cache;            // per kernel instantiation, per device
-    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI>, (size_t)C::SMEM_BYTES, smem_cache);
+    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS>, (size_t)C::SMEM_BYTES, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  const long long total_ll = (long long)p.m_tiles * p.n_tiles * p.nclasses;
+  if (NS > 1) build_fusion(p, NS); else p.fuse = 0;
+  const long long total_ll = (long long)p.m_tiles * p.n_tiles * (NS > 1 ? p.ngroups : p.nclasses);
   if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
   const int total = (int)total_ll;
   p.fd_tiles_per_class = fast_div_magic((unsigned)(p.m_tiles * p.n_tiles));
   p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
   p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
   const int grid = total < num_sms ? total : num_sms;
-  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
+  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI, NS>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
 }
 
-template <int BN>
+template <int BN, int NS = 1>
 int launch_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   switch (p.epi) {                          // the epilogue mode is compiled into the kernel
-    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD>(p, w, w_rows, w_cols, stream);
-    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD>(p, w, w_rows, w_cols, stream);
-    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE>(p, w, w_rows, w_cols, stream);
-    default: return launch_tc_epi<BN, EPI_RAW>(p, w, w_rows, w_cols, stream);
+    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD, NS>(p, w, w_rows, w_cols, stream);
+    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD, NS>(p, w, w_rows, w_cols, stream);
+    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE, NS>(p, w, w_rows, w_cols, stream);
+    default: return launch_tc_epi<BN, EPI_RAW, NS>(p, w, w_rows, w_cols, stream);
   }
 }
 
@@ -733,6 +885,20 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     static int force = -1;                    // developer knob: CGS_FORCE_BN=16..256 overrides the tile-width heuristic
     if (force < 0) { const char* e = getenv("CGS_FORCE_BN"); force = e ? atoi(e) : 0; }
     if (force) bn = force;
+  }
+  // class-fused instances of the transposed-type passes: taken when the fused tiles (4x / 2x fewer than class tiles)
+  // still give every SM one; CGS_DEBUG bit 1048576 forces them whenever they are legal (parity tests at small batch)
+  if (!p.force_bn) {
+    const int bn_full = pick_bn(p.N);
+    const int ns = fusion_slots(p, bn_full);
+    if (ns && ((debug_flags() & 1048576) || count_m_tiles(p) * (ns == 2 ? 2 : 1) >= num_sms)) {
+      switch (ns * 1000 + bn_full) {
+        case 4032: return launch_tc<32, 4>(p, w, w_rows, w_cols, stream);
+        case 4064: return launch_tc<64, 4>(p, w, w_rows, w_cols, stream);
+        case 2128: return launch_tc<128, 2>(p, w, w_rows, w_cols, stream);
+        default: break;
+      }
+    }
   }
   switch (bn) {
     case 16: return launch_tc<16>(p, w, w_rows, w_cols, stream);

@@ -26,6 +26,22 @@ enum : int {
 
 constexpr int kMaxTaps = 32;
 constexpr int kMaxClasses = 4;
+constexpr int kMaxShifts = 18;
+
+// Class-fused transposed passes (stride-2 deconv forward / conv data-gradient): the output-parity classes of one
+// input-grid tile read the SAME shifted input tiles (dy, dx in {-1, 0, 1}), each class with its own weights.  A fused
+// tile keeps one TMEM accumulator per class ("slot") and walks the shifts once: the A tile of a shift is fetched once
+// and multiplied with the weight tile of every class that has a tap there -- 9 A loads instead of 25 for k = 5.
+struct FuseShift {
+  signed char dy, dx;
+  unsigned char ncls;           // classes with a tap at this shift
+  unsigned char slot[4];        // their accumulator slots
+  int katom0[4];                // first K atom (32 floats) of that tap's weights; + channel block
+};
+struct FuseGroup {
+  int nshifts, shift0, ncls;    // shifts [shift0, shift0 + nshifts) of shf[]; classes in this group
+  int cls[4];                   // class index of each slot (output offsets oy0 / ox0)
+};
 
 struct GemmClass {
   int k0;      // first K element of this class inside the packed weight matrix
@@ -72,6 +88,10 @@ struct ConvGemmParams {
   // them are never scheduled, rows past them never stored.  Grids stay sized for the full batch, so the launch
   // sequence is static (CUDA-graph capturable) and no host synchronisation is needed when samples leave the batch.
   const int* live;
+  // class fusion (see FuseShift): 0 = one class per tile, else the launcher filled grp / shf
+  int fuse, ngroups;
+  FuseGroup grp[2];
+  FuseShift shf[kMaxShifts];
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
   // exact division of the persistent tile index by multiply-shift (filled by the launcher; see fast_div)
   unsigned long long fd_tiles_per_class, fd_n_tiles, fd_hy_tiles;
@@ -122,7 +142,7 @@ __device__ __forceinline__ LiveTiles live_tiles(const ConvGemmParams& p) {
     t.tiles_per_class = ((b + p.BB - 1) / p.BB) * p.hy_tiles * p.n_tiles;
     t.fd_tiles_per_class = fast_div_magic_dev((unsigned)t.tiles_per_class);
   }
-  t.total = t.tiles_per_class * p.nclasses;
+  t.total = t.tiles_per_class * (p.fuse ? p.ngroups : p.nclasses);
   return t;
 }
 

@@ -841,8 +841,11 @@ int launch_edge_pair(EdgeNarrowParams pn, const EdgeWideParams& pw, int store_im
 
 int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st) {
   if (p.B <= 0) return CGS_OK;
+  // tcgen05 form with the input patch resident in shared memory (edge_tc.cu); CGS_DEBUG bit 2097152 keeps mma.sync
+  if (!(debug_flags() & 2097152) && p.IW >= 16 && edge_narrow_tc_supported(p)) return launch_edge_narrow_tc(p, st);
   // gather form with register accumulators (edge_narrow2); CGS_DEBUG bit 262144 keeps the column-buffer kernel
-  if (!(debug_flags() & 262144) && p.K == 64 && p.pad_y == 1 && p.pad_x == 1 && p.IW <= 32 && (p.k == 4 || p.k == 5) &&
+  // (rows narrower than 16 pixels leave half of every 16-row MMA tile empty: the MNIST-sized nets keep the other form)
+  if (!(debug_flags() & 262144) && p.K == 64 && p.pad_y == 1 && p.pad_x == 1 && p.IW >= 16 && p.IW <= 32 && (p.k == 4 || p.k == 5) &&
       p.OW == 2 * p.IW && p.OH == 2 * p.IH && p.e.epi != EPI_UPDATE) {
     int warps = 8;
     narrow2_geometry(p, warps);

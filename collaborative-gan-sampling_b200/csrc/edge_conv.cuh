@@ -54,6 +54,9 @@ bool edge_wide_supported(int N, int k, int cimg);
 bool edge_narrow_supported(int K, int k, int cimg, int IW);
 int launch_edge_wide(const EdgeWideParams& p, cudaStream_t st);
 int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st);
+// the same pass on tcgen05 with the input patch resident in shared memory (edge_tc.cu)
+bool edge_narrow_tc_supported(const EdgeNarrowParams& p);
+int launch_edge_narrow_tc(const EdgeNarrowParams& p, cudaStream_t st);
 // narrow pass + the wide pass that consumes its output, one image per tile, in one kernel (edge_pair_kernel);
 // store_image = 0 keeps the intermediate image-like tensor out of global memory (backward pair)
 bool edge_pair_supported(const EdgeNarrowParams& pn, const EdgeWideParams& pw);

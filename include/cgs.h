@@ -44,7 +44,8 @@ enum cgs_status {
 #define CGS_ABI_VERSION 1
 CGS_API int cgs_version(void);
 CGS_API const char* cgs_last_error(void);
-/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence).
+ * Developer aid OUTSIDE the drop-in contract: a process-wide atomic counter, never read by any compute path. */
 CGS_API long long cgs_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -183,7 +184,9 @@ typedef struct cgs_refine_cfg {
   float vmin, vmax;
   int math;          /* cgs_math */
   int early_exit;    /* opt-in (README.md:13): a sample whose logit reaches exit_logit keeps its best state, leaves
-                        the batch and the remaining rows are compacted; costs one host sync per step; 0 = reference */
+                        the batch and the remaining rows are compacted ON THE DEVICE (the live-row count stays in
+                        device memory, grids are sized for the full batch): no host synchronisation, the launch
+                        sequence is static and CUDA-graph capturable; 0 = reference behaviour (always K steps) */
   float exit_logit;
 } cgs_refine_cfg;
 
@@ -240,10 +243,15 @@ CGS_API int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, con
 
 /* Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when env CGS_DEBUG has bit 256 set. */
 CGS_API int cgs_debug_trace(unsigned long long* out_host, int capacity);
-/* Developer aid: replace the CGS_DEBUG knobs at run time; returns the previous value.  Bit 4096 routes the image-edge
+/* Developer aid OUTSIDE the drop-in contract (process-wide atomic; the product never calls it -- only the parity
+ * tests do, to keep alternative lowerings covered): replace the CGS_DEBUG knobs at run time; returns the previous
+ * value.  Every lowering a knob selects produces the same results (bit-identical or within the stated tolerance, see
+ * tests/test_conv_gpu.py).  Bit 4096 routes the image-edge
  * passes (first D conv / last G deconv and their data-gradients) through the general tcgen05 lowerings instead of
  * the fused streaming kernels of csrc/edge_conv.cu; 65536 runs the edge passes as separate kernels instead of the
- * paired ones; 16384 disables split-K on the long fc forward; 32768 adds programmatic dependent launch. */
+ * paired ones; 16384 disables split-K on the long fc forward; 32768 adds programmatic dependent launch; 262144
+ * keeps the column-buffer form of the narrow edge kernel; 524288 disables / 1048576 forces the class-fused tcgen05
+ * tiles of the transposed-type passes. */
 CGS_API int cgs_debug_set_flags(int flags);
 
 #ifdef __cplusplus

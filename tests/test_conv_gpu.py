@@ -43,6 +43,46 @@ def test_edge_layers_general_lowering(cgs_lib, cuda_device, general_lowering, ar
     test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, "tf32")
 
 
+@pytest.fixture
+def forced_fusion(cgs_lib):
+    """Class-fused tcgen05 tiles whenever they are legal (CGS_DEBUG bit 1048576), whatever the tile count."""
+    old = cgs_lib.cgs_debug_set_flags(1048576)
+    yield
+    cgs_lib.cgs_debug_set_flags(old)
+
+
+@pytest.mark.parametrize("arch_name,B", [("dcgan32_l1", 3), ("dcgan32_l2", 40), ("dcgan64_l2", 9), ("dcgan64_l1", 2)])
+def test_layers_class_fused_tiles(cgs_lib, cuda_device, forced_fusion, arch_name, B):
+    """The class-fused instances of the transposed-type passes (one A tile per shift feeds all parity classes) against
+    the oracle, at batches where the launcher would otherwise pick one class per tile."""
+    test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, "tf32")
+
+
+@pytest.mark.parametrize("arch_name,B,gain", [("dcgan32_l2", 6, 2.5), ("dcgan64_l1", 3, 2.5), ("dcgan32_l2", 600, 2.5),
+                                               ("dcgan32_l1", 1024, 2.5)])   # the last two: several tiles per CTA
+def test_class_fusion_is_bit_identical(cgs_lib, cuda_device, arch_name, B, gain):
+    """Fused tiles accumulate every class in the same (tap, channel block) order as the one-class tiles, so the choice
+    (which depends on the tile count, i.e. on the batch) never changes a bit: shard invariance is preserved."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 5, gain, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(4))).to(cuda_device)
+
+    def run(flags):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(3, 0.1)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            x = r.build_refiner(h0)
+            torch.cuda.synchronize()
+            return x.clone(), r.optimal_logit.clone(), r.current_feature.clone()
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    fused, plain = run(1048576), run(524288)
+    assert all(torch.equal(a, b) for a, b in zip(fused, plain))
+
+
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 @pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("mnist", 67), ("dcgan32_l1", 3), ("dcgan64_l2", 2), ("dcgan64_l2", 9)])
 def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
