@@ -47,6 +47,7 @@ struct EdgeNarrowParams {
   const float* w;     // scatter layout: [k*k*4][K], row (ky*k + kx)*4 + c
   int B, IH, IW, K, OH, OW, k, cimg, pad_y, pad_x, out_pitch, out_xoff;
   int R, halo_lo, halo_hi, bands;   // input rows per tile, extra rows read above / below, tiles per image
+  int s2d;            // 1: out (and e.aux) are in the space-to-depth image layout [B][IH][IW][16] (see edge_tc.cu)
   EdgeEpi e;
 };
 
@@ -57,6 +58,14 @@ int launch_edge_narrow(EdgeNarrowParams p, cudaStream_t st);
 // the same pass on tcgen05 with the input patch resident in shared memory (edge_tc.cu)
 bool edge_narrow_tc_supported(const EdgeNarrowParams& p);
 int launch_edge_narrow_tc(const EdgeNarrowParams& p, cudaStream_t st);
+// the wide pass (image-like input -> 64 channels, stride-2 strided type) on tcgen05 over the SPACE-TO-DEPTH image
+// layout [B][H/2][W/2][16], channel (ry * 2 + rx) * 4 + c = image pixel (2j + ry, 2i + rx, c): the k x k stride-2 conv
+// becomes a 3 x 3 stride-1 conv over 16 channels, which the resident-patch / shifted-descriptor scheme covers
+bool edge_wide_tc_supported(const EdgeWideParams& p);
+int launch_edge_wide_tc(const EdgeWideParams& p, int B, cudaStream_t st);
+// dense [B][H][W][4] <-> space-to-depth [B][H/2][W/2][16]
+int image_to_s2d(const float* dense, float* s2d, long long B, int H, int W, cudaStream_t st);
+int s2d_to_image(const float* s2d, float* dense, long long B, int H, int W, cudaStream_t st);
 // narrow pass + the wide pass that consumes its output, one image per tile, in one kernel (edge_pair_kernel);
 // store_image = 0 keeps the intermediate image-like tensor out of global memory (backward pair)
 bool edge_pair_supported(const EdgeNarrowParams& pn, const EdgeWideParams& pw);

@@ -162,7 +162,10 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
         const int v = 128 * mt + quarter * 32 + lane;          // virtual pixel of this lane
         const int jr = v / q.PW, i = v - jr * q.PW, j = j0 + jr;
         const bool valid = i < p.IW && j < j1;
-        float* obase = p.out + ((size_t)b * p.OH + 2 * j) * p.out_pitch * 4 + (size_t)(2 * i + p.out_xoff) * 4;
+        // s2d layout: the 16 accumulator columns (py, px, c) of a lane ARE one 64-byte s2d pixel (coalesced rows)
+        float* obase = p.s2d ? p.out + (((size_t)b * p.IH + j) * p.IW + i) * 16
+                             : p.out + ((size_t)b * p.OH + 2 * j) * p.out_pitch * 4 + (size_t)(2 * i + p.out_xoff) * 4;
+        const size_t py_stride = p.s2d ? 8 : (size_t)p.out_pitch * 4;      // floats between the py = 0 and py = 1 pixels
         // derivative operand (the forward image at the four output pixels): in flight while the MMAs still run
         float4 aux[2][2];
         if (bwd && valid) {
@@ -170,7 +173,7 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
 #pragma unroll
           for (int py = 0; py < 2; ++py)
 #pragma unroll
-            for (int px = 0; px < 2; ++px) aux[py][px] = __ldg(reinterpret_cast<const float4*>(abase + (size_t)py * p.out_pitch * 4 + px * 4));
+            for (int px = 0; px < 2; ++px) aux[py][px] = __ldg(reinterpret_cast<const float4*>(abase + py * py_stride + px * 4));
         }
         if (!waited) {
           mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -188,7 +191,7 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
         if (valid) {
 #pragma unroll
           for (int py = 0; py < 2; ++py) {
-            float* orow = obase + (size_t)py * p.out_pitch * 4;
+            float* orow = obase + py * py_stride;
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
               const int n0 = (py * 2 + px) * 4;
@@ -201,12 +204,14 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
               o.w = 0.f;
               *reinterpret_cast<float4*>(orow + px * 4) = o;
             }
-            // margins of the pitched layout are zeros: written by the lanes at the two ends of the row
-            if (i == 0)
-              for (int c = 0; c < p.out_xoff; ++c) *reinterpret_cast<float4*>(orow - (size_t)(p.out_xoff - c) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i == p.IW - 1)
-              for (int c = p.out_xoff + p.OW; c < p.out_pitch; ++c)
-                *reinterpret_cast<float4*>(orow + (size_t)(c - p.out_xoff - 2 * i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!p.s2d) {
+              // margins of the pitched layout are zeros: written by the lanes at the two ends of the row
+              if (i == 0)
+                for (int c = 0; c < p.out_xoff; ++c) *reinterpret_cast<float4*>(orow - (size_t)(p.out_xoff - c) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (i == p.IW - 1)
+                for (int c = p.out_xoff + p.OW; c < p.out_pitch; ++c)
+                  *reinterpret_cast<float4*>(orow + (size_t)(c - p.out_xoff - 2 * i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
       }
@@ -296,6 +301,299 @@ int launch_edge_narrow_tc(const EdgeNarrowParams& p, cudaStream_t st) {
   count_launch();
   if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_narrow_tc_kernel: %s", cudaGetErrorString(le));
   return check_launch("edge_narrow_tc_kernel");
+}
+
+
+// =====================================================================================================================
+// edge_wide_tc: image-like input (s2d layout) -> 64 channels; D's first conv forward (nsgan/ops.py:41) and the
+// data-gradient of G's last deconv (sampling/collaborator.py:31), both stride-2 "strided type" passes over the image.
+//
+// In the s2d layout the k x k stride-2 window of output pixel (oy, ox) is the 3 x 3 neighbourhood of s2d pixel (oy, ox):
+//   tap ky reads image row 2 oy + ky - pad = 2 (oy + dy) + ry  with  ky = 2 dy + ry + pad, dy in {-1, 0, 1}, ry in {0, 1}
+// so out[(oy, ox)][n] = sum_{dy, dx} s2d[oy + dy][ox + dx][0..15] . W'[dy][dx][0..15][n], W' zero where (ky, kx) falls
+// outside the kernel: K = 9 x 16.  The s2d band (+ halo) is resident in shared memory as 64-byte rows (SWIZZLE_64B), the
+// A tile of shift (dy, dx) is a descriptor start advanced by (dyi * pitch + dxi) * 64 bytes; 18 MMAs (M 128, N 64, K 8)
+// per 128 virtual pixels.  Output rows are transposed through shared memory so global traffic is 64-byte segments.
+// =====================================================================================================================
+namespace {
+
+constexpr int WT_EPI_WARPS = 8;
+constexpr int WT_THREADS = (2 + WT_EPI_WARPS) * 32;
+constexpr int WT_B_BYTES = 5 * 64 * 128;          // 18 k-steps of 8 floats -> five [64][32] SWIZZLE_128B tiles
+constexpr int WT_PITCH = 20;                      // floats per staged row of the epilogue transpose
+constexpr int WT_EPI_BYTES = WT_EPI_WARPS * 32 * WT_PITCH * 4;
+
+struct WideTcParams {
+  const float* in;
+  const float* w;
+  int B, H2, W2, k, cimg, pad;
+  int R, bands, MT, PW, PR, stage_bytes, nstages, ntiles;
+  const int* live;
+  ConvGemmParams ep;       // epilogue description (out / bias / aux / mom / policy constants), see epilogue4
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  const uint32_t lo = (smem_addr >> 4) & 0x3FFFu;
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B (8 rows x 64 B), version 1, SWIZZLE_64B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constant__ CUtensorMap tmap_in) {
+  extern __shared__ uint8_t wt_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wt_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;
+  float* smem_epi = reinterpret_cast<float*>(smem + WT_B_BYTES);
+  uint8_t* smem_a = smem + WT_B_BYTES + ((WT_EPI_BYTES + 1023) / 1024) * 1024;
+  __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_ptr_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGemmParams& ep = q.ep;
+
+  // weights -> [tile = ks / 4][n][32 floats], SWIZZLE_128B; k-step ks = shift * 2 + h holds s2d channels h*8 .. h*8+7
+  for (int idx = threadIdx.x; idx < 5 * 64 * 8; idx += WT_THREADS) {
+    const int ck = idx & 7, n = (idx >> 3) & 63, tile = idx >> 9;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = tile * 32 + ck * 4 + u;            // global k index = shift * 16 + s2d channel
+      const int sh = kk >> 4, ch = kk & 15;
+      v[u] = 0.f;
+      if (sh < 9) {
+        const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+        const int ry = ch >> 3, rx = (ch >> 2) & 1, c = ch & 3;
+        const int ky = 2 * dy + ry + q.pad, kx = 2 * dx + rx + q.pad;
+        if (c < q.cimg && ky >= 0 && ky < q.k && kx >= 0 && kx < q.k) v[u] = __ldg(q.w + (size_t)n * (q.k * 32) + ky * 32 + kx * 4 + c);
+      }
+    }
+    *reinterpret_cast<float4*>(smem_b + (tile * 64 + n) * 128 + ((ck ^ (n & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], WT_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&tmem_ptr_smem, 512);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_in);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+  int ntiles = q.ntiles;
+  if (q.live) ntiles = min(ntiles, live_images(q.live, q.B) * q.bands);
+
+  if (warp == 0) {
+    if (elect_one()) {                                          // TMA producer: one box per (image, band)
+      uint32_t stage = 0, phase = 0;
+      const uint32_t bytes = (uint32_t)q.PR * q.PW * 64u;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / q.bands;
+        const int j0 = (tile - b * q.bands) * q.R;
+        const uint32_t s = stage, ph = phase;
+        if (++stage == (uint32_t)q.nstages) { stage = 0; phase ^= 1u; }
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tma_load_4d(smem_u32(smem_a) + s * q.stage_bytes, &tmap_in, &full_bar[s], 0, -1, j0 - 1, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {                                          // MMA issuer
+      constexpr uint32_t idesc = make_idesc_tf32(128, 64);
+      const uint64_t da0 = make_smem_desc_sw64(smem_u32(smem_a));
+      const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem_b));
+      uint32_t stage = 0, phase = 0, tile_count = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_count) {
+        const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        const uint32_t s = stage;
+        mbar_wait(&full_bar[s], phase);
+        if (++stage == (uint32_t)q.nstages) { stage = 0; phase ^= 1u; }
+        tcgen05_fence_after();
+        for (int mt = 0; mt < q.MT; ++mt) {
+          const uint32_t tmem_d = tmem_base + (acc * TC_MAX_MT + mt) * 64;
+#pragma unroll
+          for (int ks = 0; ks < 18; ++ks) {
+            const int sh = ks >> 1;
+            const uint32_t row0 = 128u * mt + (uint32_t)(sh / 3) * q.PW + (uint32_t)(sh % 3);
+            const uint64_t da = da0 + (uint64_t)((s * (uint32_t)q.stage_bytes + row0 * 64u + (ks & 1) * 32u) >> 4);
+            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+            umma_tf32_ss(tmem_d, da, db, idesc, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 8 warps, two groups alternate M tiles
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+    const int group = ew >> 2;                     // warps 2-5: group 0 (quarters 2,3,0,1); warps 6-9: group 1
+    float* stg = smem_epi + ew * 32 * WT_PITCH;
+    const int c4 = lane & 3, rsub = lane >> 2;     // transposed access: 8 rows x 4 float4 per pass
+    uint32_t tile_count = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_count) {
+      const int b = tile / q.bands;
+      const int j0 = (tile - b * q.bands) * q.R;
+      const int j1 = min(q.H2, j0 + q.R);
+      const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
+      bool waited = false;
+      for (int mt = group; mt < q.MT; mt += 2) {
+        // output offsets of the 4 rows this lane stores per pass group (rows ps * 8 + rsub of the warp's 32)
+        int ro[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int v = 128 * mt + quarter * 32 + ps * 8 + rsub;
+          const int jr = v / q.PW, i = v - jr * q.PW, j = j0 + jr;
+          ro[ps] = (i < q.W2 && j < j1) ? (((b * q.H2 + j) * q.W2 + i) * 64) : -1;
+        }
+        if (!waited) {
+          mbar_wait(&tmem_full_bar[acc], acc_ph);
+          tcgen05_fence_after();
+          waited = true;
+        }
+        const uint32_t taddr = tmem_base + (acc * TC_MAX_MT + mt) * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {                        // 16 output channels at a time
+          const int n = ch * 16 + c4 * 4;
+          float4 x0[4], x1[4];
+          if (ep.epi == EPI_BWD) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) if (ro[ps] >= 0) x0[ps] = __ldg(reinterpret_cast<const float4*>(ep.aux + ro[ps] + n));
+          } else if (ep.epi == EPI_UPDATE) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps)
+              if (ro[ps] >= 0) {
+                x0[ps] = *reinterpret_cast<const float4*>(ep.out + ro[ps] + n);
+                if (!ep.sgd && !ep.first) x1[ps] = *reinterpret_cast<const float4*>(ep.mom + ro[ps] + n);
+              }
+          } else if (ep.epi == EPI_FWD) {
+            x0[0] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint32_t a[16];
+          tmem_ld_32x32b_x16(taddr + ch * 16, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<float4*>(stg + lane * WT_PITCH + q4 * 4) =
+                make_float4(__uint_as_float(a[4 * q4]), __uint_as_float(a[4 * q4 + 1]), __uint_as_float(a[4 * q4 + 2]),
+                            __uint_as_float(a[4 * q4 + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + (ps * 8 + rsub) * WT_PITCH + c4 * 4);
+            if (ro[ps] >= 0)
+              *reinterpret_cast<float4*>(ep.out + ro[ps] + n) = epilogue4(ep, ro[ps] + n, v, ep.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
+          }
+          __syncwarp();
+        }
+      }
+      // every accumulator this warp reads has been read: hand the TMEM buffer back (each of the 8 warps arrives once)
+      if (!waited) { mbar_wait(&tmem_full_bar[acc], acc_ph); tcgen05_fence_after(); }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dense [B][H][W][4] <-> s2d [B][H/2][W/2][16]: one float4 (pixel) per thread
+__global__ void __launch_bounds__(256) s2d_convert_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int W,
+                                                          long long pixels, int to_s2d) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < pixels; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const long long t = idx / W;
+    const int y = (int)(t % H);
+    const long long b = t / H;
+    const long long sidx = ((b * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1));
+    if (to_s2d) dst[sidx] = src[idx]; else dst[idx] = src[sidx];
+  }
+}
+
+}  // namespace
+
+int image_to_s2d(const float* dense, float* s2d, long long B, int H, int W, cudaStream_t st) {
+  const long long px = B * H * W;
+  long long blocks = (px + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (px > 0) { s2d_convert_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)dense, (float4*)s2d, H, W, px, 1); count_launch(); }
+  return check_launch("image_to_s2d");
+}
+int s2d_to_image(const float* s2d, float* dense, long long B, int H, int W, cudaStream_t st) {
+  const long long px = B * H * W;
+  long long blocks = (px + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (px > 0) { s2d_convert_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)s2d, (float4*)dense, H, W, px, 0); count_launch(); }
+  return check_launch("s2d_to_image");
+}
+
+bool edge_wide_tc_supported(const EdgeWideParams& p) {
+  return p.N == 64 && p.ON == 64 && (p.k == 4 || p.k == 5) && p.cimg >= 1 && p.cimg <= 3 && p.pad_y == 1 && p.pad_x == 1 &&
+         (p.IH % 2) == 0 && p.OH * 2 == p.IH && p.OW >= 8 && p.OW <= 64;
+}
+
+// p.in must be the s2d form of the image-like input; p.pitch / p.xoff are ignored
+int launch_edge_wide_tc(const EdgeWideParams& p, int B, cudaStream_t st) {
+  if (B <= 0) return CGS_OK;
+  WideTcParams q;
+  std::memset(&q, 0, sizeof(q));
+  q.in = p.in; q.w = p.w; q.B = B; q.H2 = p.OH; q.W2 = p.OW; q.k = p.k; q.cimg = p.cimg; q.pad = p.pad_y;
+  q.live = p.e.live;
+  q.PW = q.W2 + 2;
+  int bestR = 1;
+  double best = 1e30;
+  for (int R = 1; R <= 16 && R <= q.H2; ++R) {
+    const int mt = ((R - 1) * q.PW + q.W2 + 127) / 128;
+    if (mt > TC_MAX_MT) break;
+    const int bands = (q.H2 + R - 1) / R;
+    const int last = q.H2 - (bands - 1) * R;
+    const double cost = (bands - 1) * mt + ((last - 1) * q.PW + q.W2 + 127) / 128 + 0.15 * bands;
+    if (cost < best) { best = cost; bestR = R; }
+  }
+  q.R = bestR;
+  q.bands = (q.H2 + q.R - 1) / q.R;
+  q.PR = q.R + 2;
+  q.MT = ((q.R - 1) * q.PW + q.W2 + 127) / 128;
+  q.stage_bytes = ((q.PR * q.PW * 64 + 1023) / 1024) * 1024;
+  const int fixed = WT_B_BYTES + ((WT_EPI_BYTES + 1023) / 1024) * 1024 + TC_SLACK_BYTES + 2048;
+  q.nstages = (227 * 1024 - fixed) / q.stage_bytes;
+  if (q.nstages > 6) q.nstages = 6;
+  if (q.nstages < 2) return set_error(CGS_ERR_UNSUPPORTED, "edge_wide_tc: band does not fit shared memory");
+  if ((128 * q.MT + 2 * q.PW + 2) * 64 > q.stage_bytes + TC_SLACK_BYTES) return set_error(CGS_ERR_UNSUPPORTED, "edge_wide_tc: slack too small");
+  const long long tiles = (long long)B * q.bands;
+  if (tiles >= (1ll << 31) || (long long)B * q.H2 * q.W2 * 64 >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "batch too large; split the batch");
+  q.ntiles = (int)tiles;
+  // epilogue description in the GEMM kernels' terms
+  ConvGemmParams& ep = q.ep;
+  ep.out = p.out; ep.bias = p.e.bias; ep.aux = p.e.aux; ep.mom = p.e.mom;
+  ep.epi = p.e.epi; ep.act_tanh = p.e.act_tanh; ep.slope = p.e.slope; ep.round_out = p.e.round_out;
+  ep.first = p.e.first; ep.clip = p.e.clip; ep.sgd = p.e.sgd; ep.rate = p.e.rate; ep.alpha = p.e.alpha; ep.vmin = p.e.vmin; ep.vmax = p.e.vmax;
+  PFN_encodeTiledTc enc = encode_fn();
+  if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {16, (cuuint64_t)q.W2, (cuuint64_t)q.H2, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {16 * 4, (cuuint64_t)q.W2 * 16 * 4, (cuuint64_t)q.H2 * q.W2 * 16 * 4};
+  cuuint32_t box[4] = {16, (cuuint32_t)q.PW, (cuuint32_t)q.PR, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (edge_wide_tc) failed (%d)", (int)r);
+  const size_t smem = (size_t)fixed - 2048 + (size_t)q.nstages * q.stage_bytes + 1024;
+  static DynSmemCache smem_cache;
+  cudaError_t e = ensure_dyn_smem(edge_wide_tc_kernel, smem, smem_cache);
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_wide_tc): %s", cudaGetErrorString(e));
+  long long grid = tiles < device_num_sms() ? tiles : device_num_sms();
+  cudaError_t le = launch_pdl(edge_wide_tc_kernel, dim3((unsigned)grid), dim3(WT_THREADS), smem, st, q, tmap);
+  count_launch();
+  if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_wide_tc_kernel: %s", cudaGetErrorString(le));
+  return check_launch("edge_wide_tc_kernel");
 }
 
 }  // namespace cgs

@@ -218,6 +218,10 @@ int make_backward_params(const cgs_layer_desc& L, int64_t B, const float* dy, fl
 // ---------------------------------------------------------------------------------------------
 constexpr int IMG_XOFF = 2;
 inline int img_pitch(int w) { return w + 8; }
+// layout of an image-like tensor handed to / produced by a pass
+enum : int { IMG_PITCHED = 0,   // [B][H][W + 8][4] (inside the chain, mma.sync edge kernels / general lowerings)
+             IMG_DENSE = 1,     // [B][H][W][4]     (single-layer entry points)
+             IMG_S2D = 2 };     // [B][H/2][W/2][16] space-to-depth (inside the chain, tcgen05 edge kernels: edge_tc.cu)
 inline size_t tensor_elems(int h, int w, int c) {        // per-sample elements of an activation inside the chain
   return c <= 4 ? (size_t)h * img_pitch(w) * 4 : (size_t)h * w * cstride(c);
 }
@@ -497,7 +501,7 @@ int launch_splitk_reduce(ConvGemmParams pe, const float* part, int S, int64_t B,
 // Parameters of the fused image-edge kernels (edge_conv.cuh) for a scatter- / window-lowered pass; false when the
 // shape is not covered (the general tcgen05 lowering runs instead) or the kernels are switched off.
 bool make_edge_narrow(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
-                      bool dense_image, int w_cols, EdgeNarrowParams& q) {
+                      int img_mode, int w_cols, EdgeNarrowParams& q) {
   const LayerShape s = layer_shape(L);
   const int kch = backward ? L.cout : L.cin, cimg = backward ? L.cin : L.cout;
   const int iw = backward ? s.wout : L.win;
@@ -513,8 +517,9 @@ bool make_edge_narrow(const cgs_layer_desc& L, bool backward, int64_t B, const f
     q.IH = s.hout; q.IW = s.wout; q.OH = L.hin; q.OW = L.win;
     q.pad_y = same_pad_before(L.hin, L.k); q.pad_x = same_pad_before(L.win, L.k);
   }
-  q.out_pitch = dense_image ? q.OW : img_pitch(q.OW);
-  q.out_xoff = dense_image ? 0 : IMG_XOFF;
+  q.out_pitch = img_mode == IMG_PITCHED ? img_pitch(q.OW) : q.OW;
+  q.out_xoff = img_mode == IMG_PITCHED ? IMG_XOFF : 0;
+  q.s2d = img_mode == IMG_S2D;
   q.e = make_edge_epi(e, L.bias);
   return true;
 }
@@ -555,7 +560,7 @@ int try_edge_pair(const cgs_layer_desc& ln, const cgs_layer_desc& lw, bool backw
 
 // One layer pass (forward or data-gradient) with its fused epilogue; picks the gather or the scatter lowering.
 int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in, float* out, const PassEpi& e,
-             float* col, int math, cudaStream_t st, bool dense_image = false, bool defer_reduce = false) {
+             float* col, int math, cudaStream_t st, int img_mode = IMG_PITCHED, bool defer_reduce = false) {
   const float* w = backward ? L.w_bwd : L.w_fwd;
   const int rows = backward ? L.rows_bwd : L.rows_fwd;
   const int cols = backward ? L.kcols_bwd : L.kcols_fwd;
@@ -565,8 +570,9 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
     if (rows != scatter_cols(L)) return set_error(CGS_ERR_INVALID, "weights of this pass must be in scatter layout (%d rows)", scatter_cols(L));
     {
       EdgeNarrowParams q;
-      if (math == CGS_MATH_TF32_TENSOR && !e.upd && make_edge_narrow(L, backward, B, in, out, e, dense_image, cols, q))
+      if (math == CGS_MATH_TF32_TENSOR && !e.upd && make_edge_narrow(L, backward, B, in, out, e, img_mode, cols, q))
         return launch_edge_narrow(q, st);
+      if (img_mode == IMG_S2D) return set_error(CGS_ERR_UNSUPPORTED, "s2d image layout needs the tcgen05 edge kernels");
     }
     ConvGemmParams p;
     if (int rc = make_scatter_gemm_params(L, backward, B, in, col, p)) return rc;
@@ -591,8 +597,8 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
       c.IH = s.hout; c.IW = s.wout; c.OH = L.hin; c.OW = L.win;
       c.pad_y = same_pad_before(L.hin, L.k); c.pad_x = same_pad_before(L.win, L.k);
     }
-    c.out_pitch = dense_image ? c.OW : img_pitch(c.OW);
-    c.out_xoff = dense_image ? 0 : IMG_XOFF;
+    c.out_pitch = img_mode == IMG_PITCHED ? img_pitch(c.OW) : c.OW;
+    c.out_xoff = img_mode == IMG_PITCHED ? IMG_XOFF : 0;
     c.pixels = (long long)B * c.OH * c.out_pitch;
     c.live = e.live;
     long long blocks = (c.pixels + 255) / 256;
@@ -640,6 +646,11 @@ int run_pass(const cgs_layer_desc& L, bool backward, int64_t B, const float* in,
       return set_error(CGS_ERR_INVALID, "weights of this pass must be in window layout (%d columns)", window_kcols(L));
     if (int rc = make_window_params(L, backward, B, in, out, p)) return rc;
     EdgeWideParams q;
+    if (img_mode == IMG_S2D) {               // image-like input in s2d layout: tcgen05 resident-patch kernel
+      if (math == CGS_MATH_TF32_TENSOR && make_edge_wide(L, backward, B, in, out, e, p, q) && edge_wide_tc_supported(q))
+        return launch_edge_wide_tc(q, (int)B, st);
+      return set_error(CGS_ERR_UNSUPPORTED, "s2d image layout needs the tcgen05 edge kernels");
+    }
     if (math == CGS_MATH_TF32_TENSOR && make_edge_wide(L, backward, B, in, out, e, p, q)) return launch_edge_wide(q, st);
   } else if (int rc = backward ? make_backward_params(L, B, in, out, p) : make_forward_params(L, B, in, out, p)) {
     return rc;
@@ -680,6 +691,7 @@ struct HeadParams {
   float* best_feature;
   int img_elems, feat_elems;   // dense per-sample sizes (what the caller sees)
   int img_h, img_w4, img_pitch4, img_xoff4;   // chain-side image layout in float4 units (pitched if <= 4 channels)
+  int img_s2d;          // chain-side image is in the space-to-depth layout [H/2][W/2][16] (tcgen05 edge kernels)
   float* cur_logit;     // [B]
   float* best_logit;    // [B]
   float* best_step;     // [B]
@@ -793,11 +805,21 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   }
   if (s_update & 1) {
     // chain-side image rows (possibly pitched) -> dense best_img
-    const float4* src = reinterpret_cast<const float4*>(p.img) + (size_t)b * p.img_h * p.img_pitch4 + p.img_xoff4;
     float4* dst = reinterpret_cast<float4*>(p.best_img + (size_t)ob * p.img_elems);
-    for (int i = threadIdx.x; i < p.img_h * p.img_w4; i += 256) {
-      const int y = i / p.img_w4;
-      dst[i] = src[(size_t)y * p.img_pitch4 + (i - y * p.img_w4)];
+    if (p.img_s2d) {
+      // s2d pixel (y/2, x/2), sub-pixel (y & 1, x & 1) -> dense pixel (y, x); img_w4 = W here (one float4 per pixel)
+      const float4* src = reinterpret_cast<const float4*>(p.img) + (size_t)b * p.img_h * p.img_w4;
+      const int W = p.img_w4;
+      for (int i = threadIdx.x; i < p.img_h * W; i += 256) {
+        const int y = i / W, x = i - y * W;
+        dst[i] = src[((size_t)(y >> 1) * (W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))];
+      }
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(p.img) + (size_t)b * p.img_h * p.img_pitch4 + p.img_xoff4;
+      for (int i = threadIdx.x; i < p.img_h * p.img_w4; i += 256) {
+        const int y = i / p.img_w4;
+        dst[i] = src[(size_t)y * p.img_pitch4 + (i - y * p.img_w4)];
+      }
     }
     if (p.best_feature) {
       const float4* fs = reinterpret_cast<const float4*>(p.feature + (size_t)b * p.feat_elems);
@@ -935,6 +957,22 @@ static int build_chain(const cgs_net_desc* gtail, const cgs_net_desc* d, Chain& 
   return CGS_OK;
 }
 
+// Image-like tensors of the chain live in the s2d layout when both image-edge layers run on the tcgen05 edge kernels
+// (edge_tc.cu): G's last deconv (64 -> <= 3 channels) and D's first conv (<= 3 -> 64 channels), rows of >= 16 pixels.
+// CGS_DEBUG bits 4096 (general lowerings) and 2097152 (mma.sync edge kernels) keep the pitched layout.
+static bool chain_s2d(const Chain& c, int math) {
+  if (math != CGS_MATH_TF32_TENSOR || (debug_flags() & (4096 | 2097152))) return false;
+  if (c.n_gtail < 1 || c.n_gtail >= c.n) return false;
+  const cgs_layer_desc& Ln = c.layers[c.n_gtail - 1];
+  const cgs_layer_desc& Lw = c.layers[c.n_gtail];
+  if (Ln.type != CGS_LAYER_DECONV || Lw.type != CGS_LAYER_CONV) return false;
+  if (Ln.cin != 64 || Ln.cout > 3 || Lw.cout != 64 || Lw.cin != Ln.cout) return false;
+  if ((Ln.k != 4 && Ln.k != 5) || (Lw.k != 4 && Lw.k != 5)) return false;
+  if (Ln.win < 16 || Ln.win > 64 || Ln.hin != Ln.win || Lw.hin != 2 * Ln.hin || Lw.win != 2 * Ln.win) return false;
+  if (same_pad_before(Lw.hin, Lw.k) != 1 || same_pad_before(2 * Ln.hin, Ln.k) != 1) return false;
+  return true;
+}
+
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct Workspace {
@@ -985,6 +1023,7 @@ static bool head_takes_partials(const Chain& c, const Workspace& w, int64_t B, i
 
 static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, cudaStream_t st,
                        const int* live = nullptr) {
+  const int img_mode = chain_s2d(c, math) ? IMG_S2D : IMG_PITCHED;
   for (int i = 0; i < c.n; ++i) {
     PassEpi e;
     e.live = live;
@@ -993,7 +1032,7 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
     // TF32 path: activations that feed another MMA are rounded to TF32 (RN) where they are produced, so the
     // tensor core's operand truncation is exact; the image (returned to the caller) and the head input stay FP32
     e.round_out = (math == CGS_MATH_TF32_TENSOR) && (i != c.n_gtail - 1) && (i != c.n - 1);
-    if (i == c.n_gtail - 1 && i + 1 < c.n) {
+    if (i == c.n_gtail - 1 && i + 1 < c.n && img_mode == IMG_PITCHED) {
       // generator's last deconv + discriminator's first conv on the same image: one kernel when the shapes allow
       PassEpi e2;
       e2.live = live;
@@ -1005,7 +1044,7 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
       if (rc == 1) { ++i; continue; }
     }
     const bool defer = (i == c.n - 1) && head_takes_partials(c, w, B, math);
-    if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st, false, defer)) return rc;
+    if (int rc = run_pass(c.layers[i], false, B, w.act[i], w.act[i + 1], e, w.col, math, st, img_mode, defer)) return rc;
   }
   return CGS_OK;
 }
@@ -1014,6 +1053,7 @@ static int run_forward(const Chain& c, const Workspace& w, int64_t B, int math, 
 // the last GEMM's epilogue; otherwise the raw gradient is written to grad_out.
 static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math, const ConvGemmParams* upd,
                         float* grad_out, cudaStream_t st, const int* live = nullptr) {
+  const int img_mode = chain_s2d(c, math) ? IMG_S2D : IMG_PITCHED;
   int cur = 0;
   for (int i = c.n - 1; i >= 0; --i) {
     float* dst = (i == 0) ? (upd ? w.act[0] : grad_out) : w.g[cur ^ 1];
@@ -1027,7 +1067,7 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
     } else {
       e.upd = upd;
     }
-    if (i == c.n_gtail && i >= 1) {
+    if (i == c.n_gtail && i >= 1 && img_mode == IMG_PITCHED) {
       // data-gradients of D's first conv and G's last deconv: one kernel, the image gradient never leaves the SM
       PassEpi e2;
       e2.live = live;
@@ -1045,7 +1085,7 @@ static int run_backward(const Chain& c, const Workspace& w, int64_t B, int math,
       if (rc < 0) return rc;
       if (rc == 1) { --i; cur ^= 1; continue; }
     }
-    if (int rc = run_pass(c.layers[i], true, B, w.g[cur], dst, e, w.col, math, st)) return rc;
+    if (int rc = run_pass(c.layers[i], true, B, w.g[cur], dst, e, w.col, math, st, img_mode)) return rc;
     cur ^= 1;
   }
   return CGS_OK;
@@ -1096,6 +1136,10 @@ static int head_launch(const Chain& c, const Workspace& w, int64_t B, HeadParams
     hp.img_pitch4 = (pitched ? img_pitch(si.wout) : si.wout) * c4;
     hp.img_xoff4 = pitched ? IMG_XOFF * c4 : 0;
     hp.img_elems = si.hout * si.wout * si.cs_out;
+    if (chain_s2d(c, math)) {
+      hp.img_s2d = 1;
+      hp.img_w4 = si.wout;                      // one float4 per pixel
+    }
   }
   hp.feature = w.act[0];
   hp.feat_elems = (int)c.act_elems[0];
@@ -1243,7 +1287,9 @@ extern "C" int cgs_forward_logits_and_grad(const cgs_net_desc* gtail, const cgs_
   if (img_out) {
     const cgs_layer_desc& Li = c.layers[c.n_gtail - 1];
     const LayerShape si = layer_shape(Li);
-    if (Li.cout <= 4) {
+    if (Li.cout <= 4 && chain_s2d(c, math)) {
+      if (int rc = s2d_to_image(w.act[c.n_gtail], img_out, B, si.hout, si.wout, st)) return rc;
+    } else if (Li.cout <= 4) {
       if (int rc = unpad_image(w.act[c.n_gtail], img_out, B, si.hout, si.wout, st)) return rc;
     } else {
       cudaMemcpyAsync(img_out, w.act[c.n_gtail], (size_t)B * c.act_elems[c.n_gtail] * 4, cudaMemcpyDeviceToDevice, st);
@@ -1282,13 +1328,26 @@ static int layer_pass_dense(const cgs_layer_desc& L, bool backward, int math, in
   size_t ce = scatter_col_elems(L, false);
   if (scatter_col_elems(L, true) > ce) ce = scatter_col_elems(L, true);
   float* stage = base + ((ce * (size_t)B + 63) & ~size_t(63));
+  int img_mode = IMG_DENSE;
   if (use_window(L, backward)) {
     const LayerShape s = layer_shape(L);
     const int h = backward ? s.hout : L.hin, w = backward ? s.wout : L.win;
-    if (int rc = pad_image(in, stage, B, h, w, st)) return rc;
+    // the image-like input is re-laid out first (inside the chain it is produced in that layout: no copy there)
+    ConvGemmParams wp;
+    EdgeWideParams q;
+    const bool tc = math == CGS_MATH_TF32_TENSOR && !(debug_flags() & (4096 | 2097152)) && w >= 32 && w <= 128 &&
+                    make_window_params(L, backward, B, in, out, wp) == CGS_OK && make_edge_wide(L, backward, B, in, out, e, wp, q) &&
+                    edge_wide_tc_supported(q);
+    if (tc) {
+      if (int rc = image_to_s2d(in, stage, B, h, w, st)) return rc;
+      img_mode = IMG_S2D;
+    } else {
+      if (int rc = pad_image(in, stage, B, h, w, st)) return rc;
+      img_mode = IMG_PITCHED;                 // (the window passes read the pitched layout; their output is not image-like)
+    }
     in = stage;
   }
-  return run_pass(L, backward, B, in, out, e, col, math, st, /*dense_image=*/true);
+  return run_pass(L, backward, B, in, out, e, col, math, st, img_mode);
 }
 
 extern "C" int cgs_layer_forward(const cgs_layer_desc* L, int math, int64_t B, const float* x, float* y,
