@@ -32,7 +32,8 @@ namespace cgs {
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 12;                // three groups of four epilogue warps (one TMEM lane quarter each)
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_MAX_MT = 4;                   // M tiles (128 virtual pixels) per band
 constexpr int TC_B_BYTES = 9 * 2 * 16 * 128;   // weights: [shift][channel half][16 columns][32 k] = 36 KB
 constexpr int TC_SLACK_BYTES = 16 * 1024;      // rows a (never stored) virtual pixel past the band may read
@@ -55,6 +56,10 @@ __device__ __forceinline__ float epilogue1_tc(const EdgeEpi& e, float a, float x
   return e.round_out ? tf32_rn(o) : o;
 }
 
+// PW (patch pitch = IW + 2) is a template parameter so that every per-MMA descriptor offset is an immediate: the
+// single MMA-issuing thread is the serial resource of this kernel (216 MMAs per band), and with run-time offsets each
+// MMA cost ~50 cycles of 64-bit address arithmetic and register -> uniform-register moves (11 k cycles per band).
+template <int PW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_constant__ CUtensorMap tmap_in) {
   const EdgeNarrowParams& p = q.p;
@@ -79,7 +84,7 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   fence_proxy_async_smem();                                  // generic-proxy weight stores -> tensor-core reads
@@ -127,14 +132,17 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
           mbar_wait(&full_bar[s], phase);
           if (++stage == (uint32_t)q.nstages) { stage = 0; phase ^= 1u; }
           tcgen05_fence_after();
+          const uint64_t da_stage = da0 + (uint64_t)((s * (uint32_t)q.stage_bytes) >> 4);
+          const uint64_t db_half = db0 + (uint64_t)(h * ((16 * 128) >> 4));
           for (int mt = 0; mt < q.MT; ++mt) {
             const uint32_t tmem_d = tmem_base + (acc * TC_MAX_MT + mt) * 16;
+            const uint64_t da_mt = da_stage + (uint64_t)(mt * ((128 * 128) >> 4));
 #pragma unroll
             for (int sh = 0; sh < 9; ++sh) {
-              // rows of the A tile = stored pixels 128 mt + (dyi * PW + dxi) ..: descriptor start in 16-byte units
-              const uint32_t row0 = 128u * mt + (uint32_t)(sh / 3) * q.PW + (uint32_t)(sh % 3);
-              const uint64_t da = da0 + (uint64_t)((s * (uint32_t)q.stage_bytes + row0 * 128u) >> 4);
-              const uint64_t db = db0 + (uint64_t)(((sh * 2 + h) * 16 * 128) >> 4);
+              // rows of the A tile = stored pixels 128 mt + dyi * PW + dxi ..: descriptor start in 16-byte units
+              constexpr int kRow = 128 >> 4;
+              const uint64_t da = da_mt + (uint64_t)(((sh / 3) * PW + (sh % 3)) * kRow);
+              const uint64_t db = db_half + (uint64_t)(sh * ((2 * 16 * 128) >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (h > 0 || sh > 0 || k > 0) ? 1u : 0u);
@@ -146,8 +154,12 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2-5: TMEM lane quarter = warp % 4)
+    // ------------------------------------------------------------------ epilogue: 12 warps (TMEM lane quarter = warp % 4);
+    // the three groups of four take the band's M tiles in turn -- the per-pixel epilogue (12 tanh, stores) is a long
+    // dependent instruction stream, so warps in flight are what buys throughput here
     const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
+    constexpr int NGROUPS = TC_EPI_WARPS / 4;
     const bool bwd = p.e.epi == EPI_BWD;
     const float4 bias4 = (p.e.epi == EPI_FWD && p.e.bias) ? __ldg(reinterpret_cast<const float4*>(p.e.bias))
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -158,7 +170,7 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
       const int j1 = min(p.IH, j0 + q.R);
       const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
       bool waited = false;
-      for (int mt = 0; mt < q.MT; ++mt) {
+      for (int mt = group; mt < q.MT; mt += NGROUPS) {
         const int v = 128 * mt + quarter * 32 + lane;          // virtual pixel of this lane
         const int jr = v / q.PW, i = v - jr * q.PW, j = j0 + jr;
         const bool valid = i < p.IW && j < j1;
@@ -183,7 +195,7 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
         uint32_t a[16];
         tmem_ld_32x32b_x16(tmem_base + (acc * TC_MAX_MT + mt) * 16 + (static_cast<uint32_t>(quarter * 32) << 16), a);
         tmem_ld_wait();
-        if (mt == q.MT - 1) {                                  // accumulators read: hand the TMEM buffer back
+        if (mt + NGROUPS >= q.MT) {                            // this warp's last accumulator read of the band
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -215,6 +227,13 @@ edge_narrow_tc_kernel(const __grid_constant__ NarrowTcParams q, const __grid_con
           }
         }
       }
+      if (group >= q.MT) {                                     // no M tile for this group in the band: arrive all the same
+        mbar_wait(&tmem_full_bar[acc], acc_ph);
+        tcgen05_fence_after();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
   }
   tcgen05_fence_before();
@@ -241,7 +260,7 @@ PFN_encodeTiledTc encode_fn() {
 }  // namespace
 
 bool edge_narrow_tc_supported(const EdgeNarrowParams& p) {
-  return p.K == 64 && p.pad_y == 1 && p.pad_x == 1 && p.IW >= 8 && p.IW <= 64 && (p.k == 4 || p.k == 5) &&
+  return p.K == 64 && p.pad_y == 1 && p.pad_x == 1 && (p.IW == 16 || p.IW == 32 || p.IW == 64) && (p.k == 4 || p.k == 5) &&
          p.OW == 2 * p.IW && p.OH == 2 * p.IH && p.e.epi != EPI_UPDATE && p.cimg >= 1 && p.cimg <= 3;
 }
 
@@ -293,11 +312,23 @@ int launch_edge_narrow_tc(const EdgeNarrowParams& p, cudaStream_t st) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (edge_narrow_tc) failed (%d)", (int)r);
   const size_t smem = (size_t)TC_B_BYTES + (size_t)q.nstages * q.stage_bytes + TC_SLACK_BYTES + 1024;
-  static DynSmemCache smem_cache;
-  cudaError_t e = ensure_dyn_smem(edge_narrow_tc_kernel, smem, smem_cache);
-  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_narrow_tc): %s", cudaGetErrorString(e));
   long long grid = tiles < device_num_sms() ? tiles : device_num_sms();
-  cudaError_t le = launch_pdl(edge_narrow_tc_kernel, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, q, tmap);
+  cudaError_t e = cudaSuccess, le = cudaSuccess;
+#define CGS_NARROW_TC_CASE(PWV)                                                                                          \
+  case PWV: {                                                                                                            \
+    static DynSmemCache smem_cache;                                                                                      \
+    e = ensure_dyn_smem(edge_narrow_tc_kernel<PWV>, smem, smem_cache);                                                   \
+    if (e == cudaSuccess)                                                                                                \
+      le = launch_pdl(edge_narrow_tc_kernel<PWV>, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, q, tmap);           \
+  } break;
+  switch (q.PW) {
+    CGS_NARROW_TC_CASE(18)
+    CGS_NARROW_TC_CASE(34)
+    CGS_NARROW_TC_CASE(66)
+    default: return set_error(CGS_ERR_UNSUPPORTED, "edge_narrow_tc: row width %d", p.IW);
+  }
+#undef CGS_NARROW_TC_CASE
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_narrow_tc): %s", cudaGetErrorString(e));
   count_launch();
   if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_narrow_tc_kernel: %s", cudaGetErrorString(le));
   return check_launch("edge_narrow_tc_kernel");
@@ -317,11 +348,17 @@ int launch_edge_narrow_tc(const EdgeNarrowParams& p, cudaStream_t st) {
 // =====================================================================================================================
 namespace {
 
-constexpr int WT_EPI_WARPS = 8;
+constexpr int WT_EPI_WARPS = 12;                 // three groups of four (one TMEM lane quarter each)
 constexpr int WT_THREADS = (2 + WT_EPI_WARPS) * 32;
 constexpr int WT_B_BYTES = 5 * 64 * 128;          // 18 k-steps of 8 floats -> five [64][32] SWIZZLE_128B tiles
 constexpr int WT_PITCH = 20;                      // floats per staged row of the epilogue transpose
-constexpr int WT_EPI_BYTES = WT_EPI_WARPS * 32 * WT_PITCH * 4;
+constexpr int WT_EPI_BYTES = WT_EPI_WARPS * 2 * 32 * WT_PITCH * 4;   // two staging tiles per warp
+
+// CTA-0 event trace (CGS_DEBUG bit 256): g_tc_trace[role][tile] = clock; dumped by cgs_debug_trace_tc
+__device__ long long g_tc_trace[8][64];
+__device__ __forceinline__ void tc_trace(int debug, int role, unsigned tile) {
+  if ((debug & 256) && blockIdx.x == 0 && tile < 64) g_tc_trace[role][tile] = clock64();
+}
 
 struct WideTcParams {
   const float* in;
@@ -338,6 +375,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// PW: patch pitch (see edge_narrow_tc_kernel); EPI: epilogue mode compiled in (the per-element epilogue is a dependent
+// instruction stream -- a run-time mode switch per float4 doubled its length)
+template <int PW, int EPI>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constant__ CUtensorMap tmap_in) {
   extern __shared__ uint8_t wt_smem_raw[];
@@ -395,6 +444,8 @@ edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constan
         const uint32_t s = stage, ph = phase;
         if (++stage == (uint32_t)q.nstages) { stage = 0; phase ^= 1u; }
         mbar_wait(&empty_bar[s], ph ^ 1);
+        tc_trace(ep.debug, 0, (unsigned)((tile - blockIdx.x) / gridDim.x));
+        if (ep.debug & 8) { mbar_arrive(&full_bar[s]); continue; }            // profiling knob: no loads
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         tma_load_4d(smem_u32(smem_a) + s * q.stage_bytes, &tmap_in, &full_bar[s], 0, -1, j0 - 1, b);
       }
@@ -408,31 +459,39 @@ edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constan
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_count) {
         const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tc_trace(ep.debug, 1, tile_count);
         const uint32_t s = stage;
         mbar_wait(&full_bar[s], phase);
+        tc_trace(ep.debug, 2, tile_count);
         if (++stage == (uint32_t)q.nstages) { stage = 0; phase ^= 1u; }
         tcgen05_fence_after();
+        const uint64_t da_stage = da0 + (uint64_t)((s * (uint32_t)q.stage_bytes) >> 4);
+        const bool no_mma = (ep.debug & 4) != 0;                              // profiling knob
         for (int mt = 0; mt < q.MT; ++mt) {
           const uint32_t tmem_d = tmem_base + (acc * TC_MAX_MT + mt) * 64;
+          const uint64_t da_mt = da_stage + (uint64_t)(mt * ((128 * 64) >> 4));
+          if (no_mma) continue;
 #pragma unroll
           for (int ks = 0; ks < 18; ++ks) {
+            constexpr int kRow = 64 >> 4;
             const int sh = ks >> 1;
-            const uint32_t row0 = 128u * mt + (uint32_t)(sh / 3) * q.PW + (uint32_t)(sh % 3);
-            const uint64_t da = da0 + (uint64_t)((s * (uint32_t)q.stage_bytes + row0 * 64u + (ks & 1) * 32u) >> 4);
-            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+            const uint64_t da = da_mt + (uint64_t)(((sh / 3) * PW + (sh % 3)) * kRow + (ks & 1) * 2);
+            const uint64_t db = db0 + (uint64_t)((ks >> 2) * (8192 >> 4) + (ks & 3) * 2);
             umma_tf32_ss(tmem_d, da, db, idesc, ks > 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);
         umma_commit(&tmem_full_bar[acc]);
+        tc_trace(ep.debug, 3, tile_count);
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: 8 warps, two groups alternate M tiles
+    // ------------------------------------------------------------------ epilogue: 12 warps, three groups take M tiles in turn
     const int ew = warp - 2;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
-    const int group = ew >> 2;                     // warps 2-5: group 0 (quarters 2,3,0,1); warps 6-9: group 1
-    float* stg = smem_epi + ew * 32 * WT_PITCH;
+    const int group = ew >> 2;                     // warps 2-5 / 6-9 / 10-13: each group covers the four quarters
+    constexpr int NGROUPS = WT_EPI_WARPS / 4;
+    const uint32_t stg = smem_u32(smem_epi) + (uint32_t)ew * (2 * 32 * WT_PITCH * 4);
     const int c4 = lane & 3, rsub = lane >> 2;     // transposed access: 8 rows x 4 float4 per pass
     uint32_t tile_count = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_count) {
@@ -441,8 +500,9 @@ edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constan
       const int j1 = min(q.H2, j0 + q.R);
       const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
       bool waited = false;
-      for (int mt = group; mt < q.MT; mt += 2) {
-        // output offsets of the 4 rows this lane stores per pass group (rows ps * 8 + rsub of the warp's 32)
+      for (int mt = group; mt < q.MT; mt += NGROUPS) {
+        const bool last_mt = mt + NGROUPS >= q.MT;
+        // output offsets of the 4 rows this lane stores per chunk (rows ps * 8 + rsub of the warp's 32)
         int ro[4];
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
@@ -450,52 +510,77 @@ edge_wide_tc_kernel(const __grid_constant__ WideTcParams q, const __grid_constan
           const int jr = v / q.PW, i = v - jr * q.PW, j = j0 + jr;
           ro[ps] = (i < q.W2 && j < j1) ? (((b * q.H2 + j) * q.W2 + i) * 64) : -1;
         }
+        // epilogue operands of all four 16-channel chunks, fetched before the accumulator wait (their latency hides
+        // behind the MMAs of this tile): forward output (derivative) / feature + momentum (policy step) / bias
+        float4 x0[4][4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int n = ch * 16 + c4 * 4;
+          if (EPI == EPI_BWD) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps)
+              x0[ch][ps] = (ro[ps] >= 0 && !(ep.debug & 2048)) ? __ldg(reinterpret_cast<const float4*>(ep.aux + ro[ps] + n))
+                                                              : make_float4(1.f, 1.f, 1.f, 1.f);   // knob 2048: no operand loads
+          } else if (EPI == EPI_FWD) {
+            x0[ch][0] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         if (!waited) {
+          if (warp == 2 && lane == 0) tc_trace(ep.debug, 4, tile_count);
           mbar_wait(&tmem_full_bar[acc], acc_ph);
           tcgen05_fence_after();
           waited = true;
+          if (warp == 2 && lane == 0) tc_trace(ep.debug, 5, tile_count);
         }
         const uint32_t taddr = tmem_base + (acc * TC_MAX_MT + mt) * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {                        // 16 output channels at a time
-          const int n = ch * 16 + c4 * 4;
-          float4 x0[4], x1[4];
-          if (ep.epi == EPI_BWD) {
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) if (ro[ps] >= 0) x0[ps] = __ldg(reinterpret_cast<const float4*>(ep.aux + ro[ps] + n));
-          } else if (ep.epi == EPI_UPDATE) {
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps)
-              if (ro[ps] >= 0) {
-                x0[ps] = *reinterpret_cast<const float4*>(ep.out + ro[ps] + n);
-                if (!ep.sgd && !ep.first) x1[ps] = *reinterpret_cast<const float4*>(ep.mom + ro[ps] + n);
-              }
-          } else if (ep.epi == EPI_FWD) {
-            x0[0] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          uint32_t a[16];
-          tmem_ld_32x32b_x16(taddr + ch * 16, a);
+        for (int cp = 0; cp < 2; ++cp) {                        // two 16-channel chunks per round
+          uint32_t a[2][16];
+          tmem_ld_32x32b_x16(taddr + (2 * cp) * 16, a[0]);
+          tmem_ld_32x32b_x16(taddr + (2 * cp + 1) * 16, a[1]);
           tmem_ld_wait();
+          if (cp == 1 && last_mt) {                             // this warp's last accumulator read of the tile
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<float4*>(stg + lane * WT_PITCH + q4 * 4) =
-                make_float4(__uint_as_float(a[4 * q4]), __uint_as_float(a[4 * q4 + 1]), __uint_as_float(a[4 * q4 + 2]),
-                            __uint_as_float(a[4 * q4 + 3]));
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              sts_f4(stg + ((u * 32 + lane) * WT_PITCH + q4 * 4) * 4,
+                     make_float4(__uint_as_float(a[u][4 * q4]), __uint_as_float(a[u][4 * q4 + 1]), __uint_as_float(a[u][4 * q4 + 2]),
+                                 __uint_as_float(a[u][4 * q4 + 3])));
           __syncwarp();
 #pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const float4 v = *reinterpret_cast<const float4*>(stg + (ps * 8 + rsub) * WT_PITCH + c4 * 4);
-            if (ro[ps] >= 0)
-              *reinterpret_cast<float4*>(ep.out + ro[ps] + n) = epilogue4(ep, ro[ps] + n, v, ep.epi == EPI_FWD ? x0[0] : x0[ps], x1[ps]);
+          for (int u = 0; u < 2; ++u) {
+            const int ch = 2 * cp + u;
+            const int n = ch * 16 + c4 * 4;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const float4 v = lds_f4(stg + ((u * 32 + ps * 8 + rsub) * WT_PITCH + c4 * 4) * 4);
+              if (ro[ps] >= 0) {
+                float4 xa = EPI == EPI_FWD ? x0[ch][0] : x0[ch][ps], xb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI == EPI_UPDATE) {         // policy step (only when the G tail is this single layer): not prefetched
+                  xa = *reinterpret_cast<const float4*>(ep.out + ro[ps] + n);
+                  if (!ep.sgd && !ep.first) xb = *reinterpret_cast<const float4*>(ep.mom + ro[ps] + n);
+                }
+                const float4 o = epilogue4_t<EPI>(ep, ro[ps] + n, v, xa, xb);
+                if (!(ep.debug & 1024)) *reinterpret_cast<float4*>(ep.out + ro[ps] + n) = o;      // knob 1024: no stores
+              }
+            }
           }
           __syncwarp();
         }
       }
-      // every accumulator this warp reads has been read: hand the TMEM buffer back (each of the 8 warps arrives once)
-      if (!waited) { mbar_wait(&tmem_full_bar[acc], acc_ph); tcgen05_fence_after(); }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (warp == 2 && lane == 0) tc_trace(ep.debug, 6, tile_count);
+      if (!waited || group >= q.MT) {
+        // a group without an M tile in this band still owes the buffer its arrivals
+        if (!waited) { mbar_wait(&tmem_full_bar[acc], acc_ph); tcgen05_fence_after(); }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
   }
   tcgen05_fence_before();
@@ -533,9 +618,14 @@ int s2d_to_image(const float* s2d, float* dense, long long B, int H, int W, cuda
   return check_launch("s2d_to_image");
 }
 
+int debug_trace_tc(long long* out_host) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out_host, g_tc_trace, sizeof(long long) * 8 * 64) == cudaSuccess ? 8 * 64 : -1;
+}
+
 bool edge_wide_tc_supported(const EdgeWideParams& p) {
   return p.N == 64 && p.ON == 64 && (p.k == 4 || p.k == 5) && p.cimg >= 1 && p.cimg <= 3 && p.pad_y == 1 && p.pad_x == 1 &&
-         (p.IH % 2) == 0 && p.OH * 2 == p.IH && p.OW >= 8 && p.OW <= 64;
+         (p.IH % 2) == 0 && p.OH * 2 == p.IH && (p.OW == 16 || p.OW == 32 || p.OW == 64);
 }
 
 // p.in must be the s2d form of the image-like input; p.pitch / p.xoff are ignored
@@ -574,6 +664,7 @@ int launch_edge_wide_tc(const EdgeWideParams& p, int B, cudaStream_t st) {
   ep.out = p.out; ep.bias = p.e.bias; ep.aux = p.e.aux; ep.mom = p.e.mom;
   ep.epi = p.e.epi; ep.act_tanh = p.e.act_tanh; ep.slope = p.e.slope; ep.round_out = p.e.round_out;
   ep.first = p.e.first; ep.clip = p.e.clip; ep.sgd = p.e.sgd; ep.rate = p.e.rate; ep.alpha = p.e.alpha; ep.vmin = p.e.vmin; ep.vmax = p.e.vmax;
+  ep.debug = debug_flags();
   PFN_encodeTiledTc enc = encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
@@ -586,11 +677,25 @@ int launch_edge_wide_tc(const EdgeWideParams& p, int B, cudaStream_t st) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled (edge_wide_tc) failed (%d)", (int)r);
   const size_t smem = (size_t)fixed - 2048 + (size_t)q.nstages * q.stage_bytes + 1024;
-  static DynSmemCache smem_cache;
-  cudaError_t e = ensure_dyn_smem(edge_wide_tc_kernel, smem, smem_cache);
-  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_wide_tc): %s", cudaGetErrorString(e));
   long long grid = tiles < device_num_sms() ? tiles : device_num_sms();
-  cudaError_t le = launch_pdl(edge_wide_tc_kernel, dim3((unsigned)grid), dim3(WT_THREADS), smem, st, q, tmap);
+  cudaError_t e = cudaSuccess, le = cudaSuccess;
+#define CGS_WIDE_TC_CASE(PWV, EPIV)                                                                                      \
+  case PWV * 8 + EPIV: {                                                                                                 \
+    static DynSmemCache smem_cache;                                                                                      \
+    e = ensure_dyn_smem(edge_wide_tc_kernel<PWV, EPIV>, smem, smem_cache);                                               \
+    if (e == cudaSuccess)                                                                                                \
+      le = launch_pdl(edge_wide_tc_kernel<PWV, EPIV>, dim3((unsigned)grid), dim3(WT_THREADS), smem, st, q, tmap);       \
+  } break;
+#define CGS_WIDE_TC_PW(PWV) CGS_WIDE_TC_CASE(PWV, EPI_FWD) CGS_WIDE_TC_CASE(PWV, EPI_BWD) CGS_WIDE_TC_CASE(PWV, EPI_UPDATE) CGS_WIDE_TC_CASE(PWV, EPI_RAW)
+  switch (q.PW * 8 + ep.epi) {
+    CGS_WIDE_TC_PW(18)
+    CGS_WIDE_TC_PW(34)
+    CGS_WIDE_TC_PW(66)
+    default: return set_error(CGS_ERR_UNSUPPORTED, "edge_wide_tc: row width %d / epilogue %d", q.W2, ep.epi);
+  }
+#undef CGS_WIDE_TC_PW
+#undef CGS_WIDE_TC_CASE
+  if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute(edge_wide_tc): %s", cudaGetErrorString(e));
   count_launch();
   if (le != cudaSuccess) return set_error(CGS_ERR_CUDA, "edge_wide_tc_kernel: %s", cudaGetErrorString(le));
   return check_launch("edge_wide_tc_kernel");
