@@ -248,6 +248,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
               const uint32_t s = stage, ph = phase;
               if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
               mbar_wait(&empty_bar[s], ph ^ 1);
+              trace(p, 1, 0, it_global);
               if (skip) {
                 mbar_arrive(&full_bar[s]);
               } else {
@@ -373,6 +374,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             mbar_wait(&full_bar[s], phase);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             tcgen05_fence_after();
+            trace(p, 2, 0, it_global);
             const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
             const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
             if (!skip_mma) {
@@ -388,6 +390,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             }
             umma_commit(&empty_bar[s]);
             if (last) umma_commit(&tmem_full_bar[acc]);
+            trace(p, 2, 1, it_global);
           }
         }
         continue;
