@@ -1,0 +1,24 @@
+"""Small end-to-end run of the image path for compute-sanitizer (memcheck / racecheck): every round-2 kernel once --
+class-fused tcgen05 tiles (forced), tcgen05 edge kernels on the s2d layout, device-side early exit, graph replay."""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "collaborative-gan-sampling_b200"))
+import torch
+from cgs import lib as L, nets as N, synthetic as S
+from sampling.collaborator import Refiner
+
+lib = L.load()
+lib.cgs_debug_set_flags(1048576)          # class-fused tiles whenever legal
+dev = torch.device("cuda", 0)
+for name, B, thr in (("dcgan64_l1", 5, None), ("dcgan32_l2", 6, None), ("dcgan64_l3", 3, 0.0), ("mnist", 20, 0.1)):
+    arch = N.get_arch(name)
+    spec = N.NetSpec(arch, S.init_weights(arch, gain=3.0 if name == "mnist" else 2.5), dev)
+    r = Refiner(3, 0.1)
+    r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    r.early_exit_logit = thr
+    h0 = torch.from_numpy(S.proposal_features(arch, B, seed=1)).to(dev)
+    x = r.build_refiner(h0)
+    torch.cuda.synchronize()
+    print(name, "ok", tuple(x.shape), float(r.optimal_logit.mean()))
+print("launches", lib.cgs_launch_count())
