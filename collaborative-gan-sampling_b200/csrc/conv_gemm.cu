@@ -58,21 +58,26 @@ constexpr int EPI_PITCH = 20;                // floats per staged row (16-byte a
 constexpr int kMaxEpiWarps = kEpiWarps + kProdWarps;              // producer warps help in TMA mode
 constexpr int EPI_STAGE_BYTES = kMaxEpiWarps * 32 * EPI_PITCH * 4;   // 30 KB
 
-template <int BN, int NS = 1>
+template <int BN, int NS = 1, int MT = 1>
 struct Cfg {
   // K blocks ("atoms" of 32 floats) per pipeline stage: the per-stage barrier handshakes of the single-thread TMA and
   // MMA roles cost ~400 cycles, so narrow tiles (short MMAs) take two atoms per stage to amortise them.  A class-fused
   // stage (NS > 1 accumulator slots per tile) is one A atom plus one weight atom per slot.
-  static constexpr int KB = (NS > 1 || BN >= 256) ? 1 : 2;
+  // MT = 2: a CTA tile is a PAIR of adjacent M tiles that share every weight atom (one A atom per M tile, one weight
+  // atom per stage): 0.75x (BN = 128) / 0.83x (BN = 64) of the L2 -> SM bytes per FLOP of one-tile stages, which is
+  // what bounds these passes (profiles/round2_ncu_summary.md C4)
+  static constexpr int KB = (NS > 1 || MT > 1 || BN >= 256) ? 1 : 2;
   static constexpr int B_ATOM_BYTES = BN * BK * 4;
-  static constexpr int A_STAGE_BYTES = KB * A_ATOM_BYTES;
+  static constexpr int A_STAGE_BYTES = (MT > 1 ? MT : KB) * A_ATOM_BYTES;
   static constexpr int B_STAGE_BYTES = (NS > 1 ? NS : KB) * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   // accumulator ring in TMEM: 4 buffers up to BN = 128 (512 columns), 2 for BN = 256; fused tiles take NS * BN
   // columns per buffer (two buffers)
-  static constexpr int ACC_COLS = NS * BN;
-  static constexpr int NACC = NS > 1 ? 512 / ACC_COLS : ((BN >= 256) ? 2 : 4);
+  static constexpr int ACC_COLS = NS * MT * BN;
+  static constexpr int NACC = (NS > 1 || MT > 1) ? 512 / ACC_COLS : ((BN >= 256) ? 2 : 4);
+  static_assert(NS == 1 || MT == 1, "class fusion and M-tile pairs are separate modes");
+  static_assert(MT == 1 || (MT == 2 && BN <= 128), "M-tile pairs need 2 * BN TMEM columns per buffer, two buffers");
   static constexpr int TMEM_COLS = NACC * ACC_COLS;
   static_assert(NS == 1 || (ACC_COLS <= 256 && BN <= 128), "fused tiles need two TMEM buffers");
   // up to BN = 128 each epilogue warp group owns whole tiles (three tile epilogues in flight per CTA, the per-tile
@@ -81,12 +86,13 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, int NS>
+template <int BN, int EPI, int NS, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a) {
-  using C = Cfg<BN, NS>;
+  using C = Cfg<BN, NS, MT>;
   constexpr bool FUSED = NS > 1;
+  constexpr bool PAIR = MT > 1;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -115,7 +121,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       // one arrive per epilogue warp that reads the buffer: the 4 warps of one group, or all groups at BN = 256
       // (fused tiles: two TMEM buffers but three epilogue groups -- whole-tile ownership would let a group run two
       //  buffer uses ahead and alias the barrier parity, so the groups share every tile's chunks instead)
-      mbar_init(&tmem_empty_bar[a], (p.a_tma && (!C::SPLIT_TILES || FUSED)) ? kMaxEpiWarps : kEpiWarps);
+      mbar_init(&tmem_empty_bar[a], (p.a_tma && (!C::SPLIT_TILES || C::NACC < 3)) ? kMaxEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -136,6 +142,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   const int total_tiles = lt.total;
   const unsigned long long fd_tpc = lt.fd_tiles_per_class;
   const int B_live = lt.B;
+  const int m_tiles_live = ((B_live + p.BB - 1) / p.BB) * p.hy_tiles;   // M tiles that hold live images
   const int rows_per_img_tile = p.BH * p.MW;   // rows one image contributes to a tile
 
   if (warp >= kEpiWarps && warp < kMmaWarp && !p.a_tma) {
@@ -315,6 +322,30 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           const int nkb = gc.nkb;
           const int cb0 = gc.cb0;
           int t = 0, cb = 0;
+          if (PAIR) {
+            // m_tile above is the PAIR index: M tiles 2 * pair and 2 * pair + 1 (the last pair may be half empty)
+            const int mt0 = 2 * m_tile;
+            const int mbA = fast_div(mt0, p.fd_hy_tiles), mbB = fast_div(mt0 + 1, p.fd_hy_tiles);
+            const int b0A = mbA * p.BB, yA = (mt0 - mbA * p.hy_tiles) * p.BH * p.S;
+            const int b0B = mbB * p.BB, yB = (mt0 + 1 - mbB * p.hy_tiles) * p.BH * p.S;
+            const bool second = mt0 + 1 < m_tiles_live;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t s = stage, ph = phase;
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              if (skip) {
+                mbar_arrive(&full_bar[s]);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], second ? 2u * a_bytes : a_bytes);
+                tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], (cb + cb0) * BK, gc.dx[t], yA + gc.dy[t], b0A);
+                if (second)
+                  tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + A_ATOM_BYTES, &tmap_a, &full_bar[s], (cb + cb0) * BK, gc.dx[t],
+                              yB + gc.dy[t], b0B);
+              }
+              if (++cb == cblocks) { cb = 0; ++t; }
+            }
+            continue;
+          }
           for (int kb = 0; kb < nkb; kb += C::KB) {
             const uint32_t s = stage, ph = phase;
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -417,6 +448,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             for (int k = 0; k < BK / 8; ++k)
               umma_tf32_ss(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
                            (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) {                        // second M tile of the pair: its own A atom, the SAME weight atom
+#pragma unroll
+              for (int k = 0; k < BK / 8; ++k)
+                umma_tf32_ss(tmem_d + BN, da + (A_ATOM_BYTES >> 4) + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
@@ -438,7 +474,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const int quarter = warp & 3;
     const int group = warp >> 2;                   // 0..2
     const int ngroups = p.a_tma ? kMaxEpiWarps / 4 : 1;
-    constexpr bool kSplitTiles = C::SPLIT_TILES && !FUSED;
+    constexpr bool kSplitTiles = C::SPLIT_TILES && C::NACC >= 3;   // whole-tile ownership needs >= 3 TMEM buffers
     const int tile_groups = kSplitTiles ? ngroups : 1;       // groups that take separate tiles
     const int chunk_groups = kSplitTiles ? 1 : ngroups;      // groups that share the chunks of one tile
     float* stage = smem_epi + warp * 32 * EPI_PITCH;
@@ -465,22 +501,23 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       if (tile >= total_tiles) break;
       const int ci = fast_div(tile, fd_tpc);
       const int rem = tile - ci * tiles_per_class;
-      const int m_tile = fast_div(rem, p.fd_n_tiles);
-      const int n_tile = rem - m_tile * p.n_tiles;
-      const int mb = fast_div(m_tile, p.fd_hy_tiles);
-      const int b0 = mb * p.BB;
-      const int j0 = (m_tile - mb * p.hy_tiles) * p.BH;
+      const int m_unit = fast_div(rem, p.fd_n_tiles);          // M tile, or M-tile pair
+      const int n_tile = rem - m_unit * p.n_tiles;
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
       // a fused tile holds one accumulator per class of its group (slots): the same epilogue runs once per slot with
       // that class's output offsets; the TMEM buffer goes back to the MMA warp after the last slot has been read
-      const int nslots = FUSED ? p.grp[ci].ncls : 1;
+      const int nslots = FUSED ? p.grp[ci].ncls : (PAIR ? (2 * m_unit + 1 < m_tiles_live ? 2 : 1) : 1);
       bool waited = false;
       for (int slot = 0; slot < nslots; ++slot) {
       const int cls_i = FUSED ? p.grp[ci].cls[slot] : ci;
       const bool last_slot = slot == nslots - 1;
+      const int m_tile = PAIR ? 2 * m_unit + slot : m_unit;    // pair mode: slot = which M tile of the pair
+      const int mb = fast_div(m_tile, p.fd_hy_tiles);
+      const int b0 = mb * p.BB;
+      const int j0 = (m_tile - mb * p.hy_tiles) * p.BH;
       // first chunk of this warp's group (rotated per slot so the three groups get equal shares of a fused tile)
-      const int chunk_first = kSplitTiles ? 0 : (FUSED ? (group + slot) % ngroups : group);
+      const int chunk_first = kSplitTiles ? 0 : ((FUSED || PAIR) ? (group + slot) % ngroups : group);
       const int t_off = ((b0 * p.OH + j0 * p.os + p.cls[cls_i].oy0) * p.OW + p.cls[cls_i].ox0) * p.ON;
       int ro[PASSES];                              // element offset of each stored row in out / aux / mom, -1 = none
 #pragma unroll
@@ -517,7 +554,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         tcgen05_fence_after();
         waited = true;
       }
-      const uint32_t taddr = tmem_base + acc * C::ACC_COLS + (FUSED ? slot * BN : 0) + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * C::ACC_COLS + ((FUSED || PAIR) ? slot * BN : 0) + (static_cast<uint32_t>(quarter * 32) << 16);
       bool released = false;
 #pragma unroll 1
       for (int ch0 = chunk_first; ch0 < nch || !released; ch0 += chunk_groups * MAXOWN) {
@@ -756,9 +793,9 @@ int fusion_slots(const ConvGemmParams& p, int bn) {
   return 0;
 }
 
-template <int BN, int EPI, int NS = 1>
+template <int BN, int EPI, int NS = 1, int MT = 1>
 int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
-  using C = Cfg<BN, NS>;
+  using C = Cfg<BN, NS, MT>;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
@@ -820,31 +857,33 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
   const int num_sms = device_num_sms();
   {
     static DynSmemCache smem_cache;            // per kernel instantiation, per device
-    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS>, (size_t)C::SMEM_BYTES, smem_cache);
+    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS, MT>, (size_t)C::SMEM_BYTES, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   if (NS > 1) build_fusion(p, NS); else p.fuse = 0;
-  const long long total_ll = (long long)p.m_tiles * p.n_tiles * (NS > 1 ? p.ngroups : p.nclasses);
+  p.m2 = MT > 1;
+  const int m_units = MT > 1 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const long long total_ll = (long long)m_units * p.n_tiles * (NS > 1 ? p.ngroups : p.nclasses);
   if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
   const int total = (int)total_ll;
-  p.fd_tiles_per_class = fast_div_magic((unsigned)(p.m_tiles * p.n_tiles));
+  p.fd_tiles_per_class = fast_div_magic((unsigned)(m_units * p.n_tiles));
   p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
   p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
   const int grid = total < num_sms ? total : num_sms;
-  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI, NS>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
+  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI, NS, MT>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
 }
 
-template <int BN, int NS = 1>
+template <int BN, int NS = 1, int MT = 1>
 int launch_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   switch (p.epi) {                          // the epilogue mode is compiled into the kernel
-    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD, NS>(p, w, w_rows, w_cols, stream);
-    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD, NS>(p, w, w_rows, w_cols, stream);
-    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE, NS>(p, w, w_rows, w_cols, stream);
-    default: return launch_tc_epi<BN, EPI_RAW, NS>(p, w, w_rows, w_cols, stream);
+    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD, NS, MT>(p, w, w_rows, w_cols, stream);
+    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD, NS, MT>(p, w, w_rows, w_cols, stream);
+    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE, NS, MT>(p, w, w_rows, w_cols, stream);
+    default: return launch_tc_epi<BN, EPI_RAW, NS, MT>(p, w, w_rows, w_cols, stream);
   }
 }
 
@@ -902,6 +941,20 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
         default: break;
       }
     }
+  }
+  // M-tile pairs sharing the weight atoms (MT = 2): 64- / 128-wide one-class tiles with a TMA'd A operand, when the
+  // pairs still give every SM a tile.  Bit-identical to single tiles (each accumulator sees the same MMA sequence).
+  // CGS_DEBUG bit 4194304 switches them off, 8388608 forces them whenever legal.
+  // (64-wide pairs save only 17 % of the bytes and measured slower on the MNIST nets: taken only when forced)
+  if (!p.force_bn && (bn == 128 || (bn == 64 && (debug_flags() & 8388608))) && p.cblocks > 0 && !p.window &&
+      !(debug_flags() & (4194304 | 512)) && p.N > bn / 2) {
+    const long long nt = (long long)((p.N + bn - 1) / bn) * p.nclasses;
+    const long long tiles = (long long)count_m_tiles(p) * nt, pairs = (long long)((count_m_tiles(p) + 1) / 2) * nt;
+    // whole rounds over the SMs: a pair round costs two tile rounds at 0.78x / 0.85x of their bytes
+    const double cost_pair = (double)((pairs + num_sms - 1) / num_sms) * 2.0 * (bn == 128 ? 0.78 : 0.85);
+    const double cost_single = (double)((tiles + num_sms - 1) / num_sms);
+    if ((debug_flags() & 8388608) || (pairs >= num_sms && cost_pair < cost_single))
+      return bn == 64 ? launch_tc<64, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 1, 2>(p, w, w_rows, w_cols, stream);
   }
   switch (bn) {
     case 16: return launch_tc<16>(p, w, w_rows, w_cols, stream);

@@ -90,6 +90,8 @@ struct ConvGemmParams {
   const int* live;
   // class fusion (see FuseShift): 0 = one class per tile, else the launcher filled grp / shf
   int fuse, ngroups;
+  // two M tiles per CTA tile (conv_gemm.cu, template MT = 2): the pair shares every weight atom of its K loop
+  int m2;
   FuseGroup grp[2];
   FuseShift shf[kMaxShifts];
   int debug;          // profiling knobs (env CGS_DEBUG): 1 = skip A gather, 2 = skip weight TMA, 4 = skip MMA issue
@@ -133,13 +135,14 @@ __device__ __forceinline__ LiveTiles live_tiles(const ConvGemmParams& p) {
   LiveTiles t;
   if (!p.live) {
     t.B = p.B;
-    t.tiles_per_class = p.m_tiles * p.n_tiles;
+    t.tiles_per_class = (p.m2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
     t.fd_tiles_per_class = p.fd_tiles_per_class;
   } else {
     int b = *reinterpret_cast<const volatile int*>(p.live);
     b = b < 0 ? 0 : (b > p.B ? p.B : b);
     t.B = b;
-    t.tiles_per_class = ((b + p.BB - 1) / p.BB) * p.hy_tiles * p.n_tiles;
+    const int mt_live = ((b + p.BB - 1) / p.BB) * p.hy_tiles;
+    t.tiles_per_class = (p.m2 ? (mt_live + 1) / 2 : mt_live) * p.n_tiles;
     t.fd_tiles_per_class = fast_div_magic_dev((unsigned)t.tiles_per_class);
   }
   t.total = t.tiles_per_class * (p.fuse ? p.ngroups : p.nclasses);

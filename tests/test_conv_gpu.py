@@ -83,6 +83,34 @@ def test_class_fusion_is_bit_identical(cgs_lib, cuda_device, arch_name, B, gain)
     assert all(torch.equal(a, b) for a, b in zip(fused, plain))
 
 
+@pytest.mark.parametrize("arch_name,B,gain", [("mnist", 40, 3.0), ("mnist", 300, 3.0), ("dcgan32_l2", 7, 2.5), ("dcgan64_l1", 3, 2.5),
+                                               ("dcgan32_l1", 1024, 2.5)])
+def test_m_tile_pairs_are_bit_identical(cgs_lib, cuda_device, arch_name, B, gain):
+    """Two M tiles per CTA sharing the weight atoms (CGS_DEBUG 8388608 forces them, 4194304 forbids them): every
+    accumulator sees the same MMA sequence, so the results are bit-identical, incl. odd tile counts (half-empty last
+    pair) and several pairs per CTA."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 5, gain, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(4))).to(cuda_device)
+
+    def run(flags):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(3, 0.1)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            x = r.build_refiner(h0)
+            torch.cuda.synchronize()
+            return x.clone(), r.optimal_logit.clone(), r.current_feature.clone()
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    paired, single = run(8388608 | 524288), run(4194304 | 524288)      # class fusion off in both: pairs everywhere legal
+    assert all(torch.equal(a, b) for a, b in zip(paired, single))
+    default = run(0)
+    assert all(torch.equal(a, b) for a, b in zip(default, single))
+
+
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 @pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("mnist", 67), ("dcgan32_l1", 3), ("dcgan64_l2", 2), ("dcgan64_l2", 9)])
 def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):
