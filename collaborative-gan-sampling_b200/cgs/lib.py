@@ -100,6 +100,7 @@ _SIGNATURES = {
     "cgs_layer_backward": (C.c_int, [C.POINTER(LayerDesc), C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cgs_debug_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "cgs_debug_trace_tc": (C.c_int, [C.c_void_p]),
     "cgs_debug_set_flags": (C.c_int, [C.c_int]),
 }
 

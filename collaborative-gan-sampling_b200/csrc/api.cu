@@ -85,4 +85,4 @@ extern "C" __attribute__((visibility("default"))) int cgs_debug_set_flags(int fl
 
 namespace cgs { int debug_trace_tc(long long* out_host); }
 // Developer aid: CTA-0 event clocks of the last edge_wide_tc launch run with CGS_DEBUG bit 256 ([8 roles][64 tiles]).
-extern "C" __attribute__((visibility("default"))) int cgs_debug_trace_tc(long long* out_host) { return cgs::debug_trace_tc(out_host); }
+extern "C" CGS_API int cgs_debug_trace_tc(long long* out_host) { return cgs::debug_trace_tc(out_host); }

@@ -243,6 +243,8 @@ CGS_API int cgs_layer_backward(const cgs_layer_desc* L, int math, int64_t B, con
 
 /* Developer aid: read (and reset) the CTA-0 pipeline event trace recorded when env CGS_DEBUG has bit 256 set. */
 CGS_API int cgs_debug_trace(unsigned long long* out_host, int capacity);
+/* Developer aid: CTA-0 event clocks of the last edge_wide_tc launch run with CGS_DEBUG bit 256 ([8 roles][64 tiles] int64). */
+CGS_API int cgs_debug_trace_tc(long long* out_host);
 /* Developer aid OUTSIDE the drop-in contract (process-wide atomic; the product never calls it -- only the parity
  * tests do, to keep alternative lowerings covered): replace the CGS_DEBUG knobs at run time; returns the previous
  * value.  Every lowering a knob selects produces the same results (bit-identical or within the stated tolerance, see
