@@ -165,8 +165,6 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const int rem = tile - ci * tiles_per_class;
       const int m_tile = rem / p.n_tiles;
       const GemmClass& gc = p.cls[ci];
-      const int nkx = gc.nkx;
-      const int nky = gc.ntaps / nkx;
       int rbase[kRowsPerThread];
       uint32_t vmask[kRowsPerThread];     // bit t set <=> tap t of this row lies inside the image
 #pragma unroll
@@ -183,12 +181,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         if (r < p.rows_valid && b < B_live && j < p.MH) {
           const int y0 = j * p.S, x0 = i * p.S;
           rbase[it] = ((b * p.IH + y0) * p.IW + x0) * p.Cs;
-          uint32_t mx = 0;
-          for (int tx = 0; tx < nkx; ++tx)
-            if ((unsigned)(x0 + gc.dx[tx]) < (unsigned)p.IW) mx |= 1u << tx;
-          uint32_t vm = 0;
-          for (int ty = 0; ty < nky; ++ty)
-            if ((unsigned)(y0 + gc.dy[ty * nkx]) < (unsigned)p.IH) vm |= mx << (ty * nkx);
+          uint32_t vm = 0;                    // (taps need not form a ky x kx grid in their enumeration order)
+          for (int tp = 0; tp < gc.ntaps; ++tp)
+            if ((unsigned)(y0 + gc.dy[tp]) < (unsigned)p.IH && (unsigned)(x0 + gc.dx[tp]) < (unsigned)p.IW) vm |= 1u << tp;
           vmask[it] = vm;
         }
       }
@@ -396,7 +391,6 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
       if (FUSED) {
         const FuseGroup& G = p.grp[ci];
-        uint32_t touched = 0;                    // slots that already hold a partial sum in this tile
         for (int si = 0; si < G.nshifts; ++si) {
           const FuseShift& sh = p.shf[G.shift0 + si];
           for (int cb = 0; cb < p.cblocks; ++cb, ++it_global) {
@@ -409,14 +403,16 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
             const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
             if (!skip_mma) {
-              for (int q = 0; q < sh.ncls; ++q) {
-                const uint32_t slot = sh.slot[q];
-                const uint32_t had = (touched >> slot) & 1u;
+              for (int r = 0; r < sh.nrun; ++r) {
+                // one MMA of N = run_len * BN columns per k-step: adjacent class slots = adjacent TMEM columns and
+                // adjacent weight atoms in the stage, the A tile is read once for all of them
+                const uint32_t slot = sh.run_slot[r];
+                const uint32_t idesc_r = make_idesc_tf32(BM, BN * sh.run_len[r]);
+                const uint32_t had = (cb > 0) ? 1u : sh.run_acc[r];
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k)
-                  umma_tf32_ss(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
+                  umma_tf32_ss(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc_r,
                                (had || k > 0) ? 1u : 0u);
-                touched |= 1u << slot;
               }
             }
             umma_commit(&empty_bar[s]);
@@ -750,26 +746,63 @@ void build_fusion(ConvGemmParams& p, int NS) {
   for (int gi = 0; gi < ngroups; ++gi) {
     FuseGroup& G = p.grp[p.ngroups++];
     G.ncls = 0;
+    // slot order (0,0), (0,1), (1,1), (1,0): classes that share a shift sit in adjacent slots (wide MMAs)
+    static const int kSlotKey[2][2] = {{0, 1}, {3, 2}};
+    int cls_of_key[4] = {-1, -1, -1, -1};
     for (int c = 0; c < p.nclasses; ++c)
-      if (NS != 2 || (p.cls[c].oy0 & 1) == order[gi]) G.cls[G.ncls++] = c;
+      if (NS != 2 || (p.cls[c].oy0 & 1) == order[gi]) cls_of_key[kSlotKey[p.cls[c].oy0 & 1][p.cls[c].ox0 & 1]] = c;
+    for (int key = 0; key < 4; ++key)
+      if (cls_of_key[key] >= 0) G.cls[G.ncls++] = cls_of_key[key];
     G.shift0 = nshf;
+    // shifts in the canonical order of the packing (refine_conv.cu fill_transposed): the first class that has a tap at
+    // a shift lists it at the position all classes agree on, so walking the taps of all classes by (users desc, dy
+    // desc, dx desc) reproduces it
+    struct Sh { int dy, dx, users; };
+    Sh cand[kMaxShifts];
+    int ncand = 0;
     for (int dy = 1; dy >= -1; --dy)
       for (int dx = 1; dx >= -1; --dx) {
-        FuseShift sh;
-        std::memset(&sh, 0, sizeof(sh));
-        sh.dy = (signed char)dy;
-        sh.dx = (signed char)dx;
-        for (int q = 0; q < G.ncls; ++q) {
-          const GemmClass& gc = p.cls[G.cls[q]];
-          for (int t = 0; t < gc.ntaps; ++t)
-            if (gc.dy[t] == dy && gc.dx[t] == dx) {
-              sh.slot[sh.ncls] = (unsigned char)q;
-              sh.katom0[sh.ncls] = (gc.k0 + t * C) / BK;
-              ++sh.ncls;
-            }
-        }
-        if (sh.ncls) p.shf[nshf++] = sh;
+        int users = 0;                              // users over ALL classes of the pass (the packing's criterion)
+        for (int c = 0; c < p.nclasses; ++c)
+          for (int t = 0; t < p.cls[c].ntaps; ++t)
+            if (p.cls[c].dy[t] == dy && p.cls[c].dx[t] == dx) ++users;
+        if (users) cand[ncand++] = Sh{dy, dx, users};
       }
+    for (int a = 1; a < ncand; ++a)
+      for (int b = a; b > 0 && cand[b].users > cand[b - 1].users; --b) { const Sh t = cand[b]; cand[b] = cand[b - 1]; cand[b - 1] = t; }
+    unsigned touched = 0;
+    for (int si = 0; si < ncand; ++si) {
+      FuseShift sh;
+      std::memset(&sh, 0, sizeof(sh));
+      sh.dy = (signed char)cand[si].dy;
+      sh.dx = (signed char)cand[si].dx;
+      for (int q = 0; q < G.ncls; ++q) {
+        const GemmClass& gc = p.cls[G.cls[q]];
+        for (int t = 0; t < gc.ntaps; ++t)
+          if (gc.dy[t] == sh.dy && gc.dx[t] == sh.dx) {
+            sh.slot[sh.ncls] = (unsigned char)q;
+            sh.katom0[sh.ncls] = (gc.k0 + t * C) / BK;
+            ++sh.ncls;
+          }
+      }
+      if (!sh.ncls) continue;
+      // runs of adjacent slots with the same accumulate state (slots are listed in ascending order)
+      for (int i = 0; i < sh.ncls;) {
+        const int first = sh.slot[i];
+        const unsigned acc = (touched >> first) & 1u;
+        int len = 1;
+        while (i + len < sh.ncls && sh.slot[i + len] == first + len && ((touched >> (first + len)) & 1u) == acc &&
+               (len + 1) * p.N <= 256)
+          ++len;
+        sh.run_slot[sh.nrun] = (unsigned char)first;
+        sh.run_len[sh.nrun] = (unsigned char)len;
+        sh.run_acc[sh.nrun] = (unsigned char)acc;
+        ++sh.nrun;
+        i += len;
+      }
+      for (int i = 0; i < sh.ncls; ++i) touched |= 1u << sh.slot[i];
+      p.shf[nshf++] = sh;
+    }
     G.nshifts = nshf - G.shift0;
   }
 }

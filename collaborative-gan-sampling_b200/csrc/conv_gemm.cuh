@@ -36,6 +36,10 @@ struct FuseShift {
   signed char dy, dx;
   unsigned char ncls;           // classes with a tap at this shift
   unsigned char slot[4];        // their accumulator slots
+  // runs of ADJACENT slots with the same accumulate state: one MMA of N = run_len * BN columns per k-step reads the
+  // A tile once for all of them (a 64-wide MMA is otherwise bound by its shared-memory operand reads, 6 KB per 32
+  // cycles of tensor work); run_acc = the slots already hold partial sums
+  unsigned char nrun, run_slot[4], run_len[4], run_acc[4];
   int katom0[4];                // first K atom (32 floats) of that tap's weights; + channel block
 };
 struct FuseGroup {

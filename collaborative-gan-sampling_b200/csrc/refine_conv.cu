@@ -98,6 +98,24 @@ void fill_transposed(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) 
   auto ntap = [&](int par, int pad) { int n = 0; for (int kk = 0; kk < k; ++kk) if (((par + pad - kk) & 1) == 0) ++n; return n; };
   if (ntap(1, pad_y) > ntap(0, pad_y)) { py_order[0] = 1; py_order[1] = 0; }
   if (ntap(1, pad_x) > ntap(0, pad_x)) { px_order[0] = 1; px_order[1] = 0; }
+  // CANONICAL SHIFT ORDER shared by all classes: a class's taps are enumerated in the order of their input shifts
+  // (dy, dx), shifts used by more classes first (ties: dy descending, dx descending).  The class-fused tcgen05 tiles
+  // (conv_gemm.cu) walk the shifts in this same order and may merge the classes of a shift into one wide MMA, so every
+  // class accumulates its taps in the same order fused or not -- results never depend on the tile choice.
+  auto has_tap = [&](int par, int pad, int d) { const int kk = par + pad - 2 * d; return kk >= 0 && kk < k; };
+  struct Shift { int dy, dx, users; };
+  Shift sh[64];
+  int nsh = 0;
+  for (int dy = 2; dy >= -2; --dy)
+    for (int dx = 2; dx >= -2; --dx) {
+      int users = 0;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          if (has_tap(py, pad_y, dy) && has_tap(px, pad_x, dx)) ++users;
+      if (users) sh[nsh++] = Shift{dy, dx, users};
+    }
+  for (int a = 1; a < nsh; ++a)                       // stable insertion sort by users, descending
+    for (int b = a; b > 0 && sh[b].users > sh[b - 1].users; --b) { const Shift t = sh[b]; sh[b] = sh[b - 1]; sh[b - 1] = t; }
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       const int py = py_order[a], px = px_order[b];
@@ -106,14 +124,11 @@ void fill_transposed(ConvGemmParams& p, int k, int pad_y, int pad_x, int cin_k) 
       g.oy0 = py;
       g.ox0 = px;
       int t = 0;
-      for (int ky = 0; ky < k; ++ky) {
-        if ((py + pad_y - ky) & 1) continue;
-        for (int kx = 0; kx < k; ++kx) {
-          if ((px + pad_x - kx) & 1) continue;
-          g.dy[t] = (signed char)((py + pad_y - ky) / 2);
-          g.dx[t] = (signed char)((px + pad_x - kx) / 2);
-          ++t;
-        }
+      for (int si = 0; si < nsh; ++si) {
+        if (!has_tap(py, pad_y, sh[si].dy) || !has_tap(px, pad_x, sh[si].dx)) continue;
+        g.dy[t] = (signed char)sh[si].dy;
+        g.dx[t] = (signed char)sh[si].dx;
+        ++t;
       }
       g.ntaps = t;
       g.nkx = ntap(px, pad_x);
