@@ -299,34 +299,70 @@ __device__ __forceinline__ bool mh_move(double d_state, bool f64_math, const voi
   }
 }
 
-// next[i+1] = first j > i that the chain would accept when its state is the score of row i (i = -1: carried state)
+// next[i+1] = first j > i that the chain would accept when its state is the score of row i (i = -1: carried state).
+// Each thread first looks at the kShortScan rows after its own (the usual gap is one or two rows); rows that are still
+// undecided after that - a sticky state whose next move is far away - are finished one at a time by the whole warp,
+// 32 candidates per step with a ballot, so a long gap costs gap/32 steps and no lane waits on a serial tail.
+constexpr int kShortScan = 8;
 __global__ void mh_next_kernel(const void* sig, int dtype, int64_t n, const double* __restrict__ uniforms,
                                uint64_t seed, uint64_t offset, const double* d_curr, const int* d_kind,
                                int* __restrict__ next) {
   const int kind = *d_kind;
   const int ushift = (kind == 0) ? 1 : 0;     // with d_curr None the first row draws no uniform (idpsampler.py:47)
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= n; t += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (n + 1 + stride - 1) / stride;       // the same trip count for every lane of a warp
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t r = 0; r < rounds; ++r, t += stride) {
+    const bool active = t <= n;
     const int64_t i = t - 1;
-    int64_t j;
-    if (i < 0 && kind == 0) {
-      j = 0;                                   // unconditional first move
-    } else {
-      double d_state;
-      bool f64_math;
-      if (i < 0) {
-        d_state = *d_curr;
-        f64_math = (dtype == CGS_F64) || (kind == 2);
+    int64_t j = n;
+    bool found = !active;
+    double d_state = 0.5;
+    bool f64_math = false;
+    if (active) {
+      if (i < 0 && kind == 0) {
+        j = 0;                                 // unconditional first move
+        found = true;
       } else {
-        d_state = load_score(sig, dtype, i);
-        f64_math = (dtype == CGS_F64);
-      }
-      for (j = i + 1; j < n; ++j) {
-        const int64_t ui = j - ushift;
-        const double u = uniforms ? uniforms[ui] : philox_uniform_f64(seed, offset + (uint64_t)ui);
-        if (mh_move(d_state, f64_math, sig, dtype, j, u)) break;
+        if (i < 0) {
+          d_state = *d_curr;
+          f64_math = (dtype == CGS_F64) || (kind == 2);
+        } else {
+          d_state = load_score(sig, dtype, i);
+          f64_math = (dtype == CGS_F64);
+        }
+        const int64_t lim = min(n, i + 1 + kShortScan);
+        for (j = i + 1; j < lim; ++j) {
+          const int64_t ui = j - ushift;
+          const double u = uniforms ? uniforms[ui] : philox_uniform_f64(seed, offset + (uint64_t)ui);
+          if (mh_move(d_state, f64_math, sig, dtype, j, u)) { found = true; break; }
+        }
+        if (j >= n) { j = n; found = true; }
       }
     }
-    next[t] = (int)j;
+    unsigned pending = __ballot_sync(0xffffffffu, !found);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const double ds = __shfl_sync(0xffffffffu, d_state, src);
+      const int fm = __shfl_sync(0xffffffffu, (int)f64_math, src);
+      const int64_t j0 = __shfl_sync(0xffffffffu, j, src);   // first row not yet examined
+      int64_t hit = n;
+      for (int64_t base = j0; base < n; base += 32) {
+        const int64_t jj = base + lane;
+        bool ok = false;
+        if (jj < n) {
+          const int64_t ui = jj - ushift;
+          const double u = uniforms ? uniforms[ui] : philox_uniform_f64(seed, offset + (uint64_t)ui);
+          ok = mh_move(ds, fm != 0, sig, dtype, jj, u);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) { hit = base + (__ffs(m) - 1); break; }
+      }
+      if (lane == src) j = hit;
+    }
+    if (active) next[t] = (int)j;
   }
 }
 

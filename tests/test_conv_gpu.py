@@ -190,7 +190,10 @@ def test_forward_logits_and_grad(cgs_lib, cuda_device, arch_name, B, gain, math)
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 @pytest.mark.parametrize("arch_name,B,K,method,gain", [("mnist", 6, 5, "momentum", 3.0), ("mnist", 3, 3, "sgd", 3.0),
                                                         ("dcgan32_l2", 4, 4, "momentum", 2.5),
-                                                        ("dcgan64_l1", 2, 3, "momentum", 2.5)])
+                                                        ("dcgan64_l1", 2, 3, "momentum", 2.5),
+                                                        # refinement at the last map: the policy step is fused into the
+                                                        # wide image-edge pass (edge_wide_tc EPI_UPDATE in TF32 mode)
+                                                        ("dcgan32_l4", 5, 3, "momentum", 2.5), ("dcgan64_l4", 2, 2, "sgd", 2.5)])
 def test_build_refiner_matches_oracle(cgs_lib, cuda_device, arch_name, B, K, method, gain, math):
     from cgs import nets as N
     from sampling.collaborator import Refiner

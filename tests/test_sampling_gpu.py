@@ -167,3 +167,35 @@ def test_mh_edge_cases(cgs_lib, cuda_device):
     emit, d, c, acc = snp.mh_chain(sig, u, np.float32(0.2), 1, 20, 0)
     assert np.array_equal(s.last_accepted.cpu().numpy().astype(bool), acc)
     assert np.array_equal(s.last_emit_src.cpu().numpy(), emit)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mh_sticky_chain(cgs_lib, cuda_device, dtype):
+    """Scores spread over many decades of 1-d: most states reject for hundreds of rows, so almost every row of
+    the successor table is finished by the warp-wide scan (sampling_kernels.cu mh_next_kernel)."""
+    from sampling.idpsampler import IndependenceSampler
+    rng = np.random.RandomState(5)
+    n = 40000
+    hi = 6 if dtype == np.float32 else 12
+    sig = (1.0 - 10.0 ** (-rng.uniform(0.5, hi, size=(n, 1)))).astype(dtype)
+    sig = np.clip(sig, 0.0, np.nextafter(dtype(1.0), dtype(0.0)))
+    for d0, u in ((dtype(0.5), rng.rand(n)), (None, rng.rand(n - 1))):
+        s = IndependenceSampler(T=3, B=2)
+        if d0 is not None:
+            s.set_score_curr(d0)
+            emit, d, c, acc = snp.mh_chain(sig, u, d0, 1, 3, 2)
+        else:
+            emit, d, c, acc = snp.mh_chain(sig, np.concatenate([[0.0], u]), None, 1, 3, 2)
+        s.sampling(np.zeros((n, 1), np.float32), sig, uniforms=u)
+        got = s.last_accepted.cpu().numpy().astype(bool)
+        assert np.array_equal(got, acc)
+        assert 1 <= acc.sum() < n // 4                     # mean gap well beyond the per-thread scan for many rows
+        assert np.array_equal(s.last_emit_src.cpu().numpy(), emit)
+        assert float(s.d_curr) == float(np.squeeze(d))
+    # counter-based uniforms through the same path
+    s = IndependenceSampler(T=0, rng="philox", seed=99)
+    s.set_score_curr(dtype(0.9))
+    s.sampling(np.zeros((n, 1), np.float32), sig)
+    u = philox_ref.philox_uniform_f64(99, np.arange(0, n, dtype=np.uint64))
+    emit, d, c, acc = snp.mh_chain(sig, u, dtype(0.9), 1, 0, 0)
+    assert np.array_equal(s.last_accepted.cpu().numpy().astype(bool), acc)
