@@ -58,7 +58,16 @@ constexpr int EPI_PITCH = 20;                // floats per staged row (16-byte a
 constexpr int kMaxEpiWarps = kEpiWarps + kProdWarps;              // producer warps help in TMA mode
 constexpr int EPI_STAGE_BYTES = kMaxEpiWarps * 32 * EPI_PITCH * 4;   // 30 KB
 
-template <int BN, int NS = 1, int MT = 1>
+template <int CG>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) umma_tf32_ss_cg2(tmem_d, da, db, idesc, accumulate); else umma_tf32_ss(tmem_d, da, db, idesc, accumulate);
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if (CG == 2) umma_commit_cg2(bar); else umma_commit(bar);
+}
+
+template <int BN, int NS = 1, int MT = 1, int CG = 1>
 struct Cfg {
   // K blocks ("atoms" of 32 floats) per pipeline stage: the per-stage barrier handshakes of the single-thread TMA and
   // MMA roles cost ~400 cycles, so narrow tiles (short MMAs) take two atoms per stage to amortise them.  A class-fused
@@ -66,8 +75,12 @@ struct Cfg {
   // MT = 2: a CTA tile is a PAIR of adjacent M tiles that share every weight atom (one A atom per M tile, one weight
   // atom per stage): 0.75x (BN = 128) / 0.83x (BN = 64) of the L2 -> SM bytes per FLOP of one-tile stages, which is
   // what bounds these passes (profiles/round2_ncu_summary.md C4)
-  static constexpr int KB = (NS > 1 || MT > 1 || BN >= 256) ? 1 : 2;
-  static constexpr int B_ATOM_BYTES = BN * BK * 4;
+  // CG = 2: the CTA is one of a PAIR (cluster of two, tcgen05 cta_group::2, M = 256): each CTA loads its own M tile
+  // and HALF the rows of every weight atom; the leader's MMAs read both halves.  Per CTA a stage is 16 KB of A plus
+  // half the weights, so the ring is 6 stages deep where single CTAs get 4 (the load latency of ~1-2 k cycles is what
+  // the 4-stage ring does not cover, profiles/round2_ncu_summary.md D1), and L2 delivers each weight byte once per pair.
+  static constexpr int KB = (NS > 1 || MT > 1 || BN >= 256 || CG > 1) ? 1 : 2;
+  static constexpr int B_ATOM_BYTES = BN * BK * 4 / CG;          // per CTA
   static constexpr int A_STAGE_BYTES = (MT > 1 ? MT : KB) * A_ATOM_BYTES;
   static constexpr int B_STAGE_BYTES = (NS > 1 ? NS : KB) * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -77,6 +90,7 @@ struct Cfg {
   static constexpr int ACC_COLS = NS * MT * BN;
   static constexpr int NACC = (NS > 1 || MT > 1) ? 512 / ACC_COLS : ((BN >= 256) ? 2 : 4);
   static_assert(NS == 1 || MT == 1, "class fusion and M-tile pairs are separate modes");
+  static_assert(CG == 1 || (CG == 2 && MT == 1), "CTA pairs replace M-tile pairs");
   static_assert(MT == 1 || (MT == 2 && BN <= 128), "M-tile pairs need 2 * BN TMEM columns per buffer, two buffers");
   static constexpr int TMEM_COLS = NACC * ACC_COLS;
   static_assert(NS == 1 || (ACC_COLS <= 256 && BN <= 128), "fused tiles need two TMEM buffers");
@@ -86,13 +100,21 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, int NS, int MT>
+template <int BN, int EPI, int NS, int MT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a) {
-  using C = Cfg<BN, NS, MT>;
+  using C = Cfg<BN, NS, MT, CG>;
   constexpr bool FUSED = NS > 1;
   constexpr bool PAIR = MT > 1;
+  constexpr bool CG2 = CG == 2;
+  // CTA pair: both CTAs walk the same tile sequence (unit = two adjacent M tiles, this CTA takes tile 2 * unit + rank);
+  // full / accumulator-free barriers live in the leader (rank 0), smem-slot-free and accumulator-full barriers are
+  // signalled in both CTAs by the leader's multicast commits
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile_first = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -121,15 +143,19 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       // one arrive per epilogue warp that reads the buffer: the 4 warps of one group, or all groups at BN = 256
       // (fused tiles: two TMEM buffers but three epilogue groups -- whole-tile ownership would let a group run two
       //  buffer uses ahead and alias the barrier parity, so the groups share every tile's chunks instead)
-      mbar_init(&tmem_empty_bar[a], (p.a_tma && (!C::SPLIT_TILES || C::NACC < 3)) ? kMaxEpiWarps : kEpiWarps);
+      // (CTA pair: the leader's barrier collects the epilogue warps of both CTAs)
+      mbar_init(&tmem_empty_bar[a], CG * ((p.a_tma && (!C::SPLIT_TILES || C::NACC < 3)) ? kMaxEpiWarps : kEpiWarps));
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+  if (warp == kMmaWarp) {
+    if (CG2) tmem_alloc_cg2(tmem_ptr_smem, C::TMEM_COLS); else tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+  }
   if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_w);
   if (warp == kTmaWarpA && lane == 0 && p.a_tma) tma_prefetch_desc(&tmap_a);
   tcgen05_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();                   // the partner's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // set-up done: let the next kernel of the chain start its own set-up, then wait for our predecessor's results
@@ -160,7 +186,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       soff[it] = r * 128 + ((chunk ^ (r & 7)) << 4);
     }
     uint32_t it_global = 0;               // K blocks issued by this thread
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
       const int ci = tile / tiles_per_class;
       const int rem = tile - ci * tiles_per_class;
       const int m_tile = rem / p.n_tiles;
@@ -233,36 +259,50 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // whole warp walks the loop (uniform control flow); one elected lane issues.  The weight matrix is viewed as
     // {32, rows, K/32} so ONE box {32, BN, KB} fetches all K atoms of a stage as consecutive atom tiles.
     const uint32_t smem_b_u32 = smem_u32(smem_b);
+    if (FUSED) {
+      // the whole warp walks the loop: lane 0 waits for the slot and posts the byte count, then lane q issues the box
+      // of the q-th class with a tap at the shift (a single thread issuing up to four boxes per stage was the slowest
+      // role of the fused tiles: 45 us of a 210 us pass)
+      const bool skip = (p.debug & 2) != 0;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
+        const int ci = fast_div(tile, fd_tpc);
+        const int rem = tile - ci * tiles_per_class;
+        const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
+        const FuseGroup& G = p.grp[ci];
+        for (int si = 0; si < G.nshifts; ++si) {
+          const FuseShift& sh = p.shf[G.shift0 + si];
+          const int ncls = sh.ncls;
+          const bool mine = lane < ncls;
+          const int q = mine ? lane : 0;
+          const uint32_t dst = (CG2 ? sh.pc_slot[cta_rank][q] : sh.slot[q]) * C::B_ATOM_BYTES;
+          const int row = n_tile * BN + (CG2 ? sh.pc_half[cta_rank][q] * (BN / 2) : 0);
+          const int katom = CG2 ? sh.pc_katom[cta_rank][q] : sh.katom0[q];
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            const uint32_t s = stage, ph = phase;
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            if (lane == 0) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              if (skip) { if (leader) mbar_arrive(&full_bar[s]); }
+              else if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ncls * CG) * C::B_ATOM_BYTES);
+            }
+            __syncwarp();
+            if (mine && !skip) {
+              if (CG2) tma_load_3d_cg2(smem_b_u32 + s * C::B_STAGE_BYTES + dst, &tmap_w, &full_bar[s], 0, row, katom + cb);
+              else tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES + dst, &tmap_w, &full_bar[s], 0, row, katom + cb);
+            }
+          }
+        }
+      }
+    } else
     if (elect_one()) {                     // one thread walks the whole loop: no per-K-block election or warp sync
       uint32_t it_global = 0;
       uint32_t stage = 0, phase = 0;
       const bool skip = (p.debug & 2) != 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
         const int ci = fast_div(tile, fd_tpc);
         const int rem = tile - ci * tiles_per_class;
         const int n_tile = rem - fast_div(rem, p.fd_n_tiles) * p.n_tiles;
-        if (FUSED) {
-          // ci = class group: per (shift, channel block) one weight atom per class that has a tap at the shift
-          const FuseGroup& G = p.grp[ci];
-          for (int si = 0; si < G.nshifts; ++si) {
-            const FuseShift& sh = p.shf[G.shift0 + si];
-            for (int cb = 0; cb < p.cblocks; ++cb, ++it_global) {
-              const uint32_t s = stage, ph = phase;
-              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-              mbar_wait(&empty_bar[s], ph ^ 1);
-              trace(p, 1, 0, it_global);
-              if (skip) {
-                mbar_arrive(&full_bar[s]);
-              } else {
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)sh.ncls * C::B_ATOM_BYTES);
-                for (int q = 0; q < sh.ncls; ++q)
-                  tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES + sh.slot[q] * C::B_ATOM_BYTES, &tmap_w, &full_bar[s], 0,
-                              n_tile * BN, sh.katom0[q] + cb);
-              }
-            }
-          }
-          continue;
-        }
         const int katom0 = p.cls[ci].k0 / BK;
         const int nkb = p.cls[ci].nkb;
         for (int kb = 0; kb < nkb; kb += C::KB, ++it_global) {
@@ -271,7 +311,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           mbar_wait(&empty_bar[s], ph ^ 1);
           trace(p, 1, 0, it_global);
           if (skip) {
-            mbar_arrive(&full_bar[s]);
+            if (leader) mbar_arrive(&full_bar[s]);
+          } else if (CG2) {                      // this CTA's half of the BN rows
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * C::B_STAGE_BYTES);
+            tma_load_3d_cg2(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], 0, n_tile * BN + (int)cta_rank * (BN / 2),
+                            katom0 + kb);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE_BYTES);
             tma_load_3d(smem_b_u32 + s * C::B_STAGE_BYTES, &tmap_w, &full_bar[s], 0, n_tile * BN, katom0 + kb);
@@ -288,11 +332,12 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         uint32_t stage = 0, phase = 0;
         const bool skip = (p.debug & 8) != 0;
         const int cblocks = p.cblocks;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
           const int ci = fast_div(tile, fd_tpc);
           const int rem = tile - ci * tiles_per_class;
-          const int m_tile = fast_div(rem, p.fd_n_tiles);
-          const int mb = fast_div(m_tile, p.fd_hy_tiles);
+          const int m_unit = fast_div(rem, p.fd_n_tiles);
+          const int m_tile = CG2 ? 2 * m_unit + (int)cta_rank : m_unit;   // (a pair's odd tile may lie past the batch:
+          const int mb = fast_div(m_tile, p.fd_hy_tiles);                 //  its box is out of range and reads zeros)
           const int b0 = mb * p.BB;
           const int y_tile = (m_tile - mb * p.hy_tiles) * p.BH * p.S;
           if (FUSED) {
@@ -304,7 +349,10 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (skip) {
-                  mbar_arrive(&full_bar[s]);
+                  if (leader) mbar_arrive(&full_bar[s]);
+                } else if (CG2) {
+                  if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * a_bytes);
+                  tma_load_4d_cg2(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, sh.dx, y_tile + sh.dy, b0);
                 } else {
                   mbar_arrive_expect_tx(&full_bar[s], a_bytes);
                   tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, sh.dx, y_tile + sh.dy, b0);
@@ -347,17 +395,22 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             const int na = (nkb - kb) < C::KB ? (nkb - kb) : C::KB;       // atoms in this stage
             mbar_wait(&empty_bar[s], ph ^ 1);
             if (skip) {
-              mbar_arrive(&full_bar[s]);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * a_bytes);
+              if (leader) mbar_arrive(&full_bar[s]);
+            } else if (leader) {
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CG * na) * a_bytes);
             }
 #pragma unroll
             for (int a = 0; a < C::KB; ++a) {
               if (a >= na) break;
               // one box = BB images x BH rows x MW columns x 32 channels; out-of-image pixels read as zero
-              if (!skip)
+              if (!skip) {
+                if (CG2)
+                  tma_load_4d_cg2(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s],
+                                  (cb + cb0) * BK, gc.dx[t], y_tile + gc.dy[t], b0);
+                else
                 tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES + a * A_ATOM_BYTES, &tmap_a, &full_bar[s],
                             (cb + cb0) * BK, gc.dx[t], y_tile + gc.dy[t], b0);
+              }
               if (++cb == cblocks) {
                 cb = 0;
                 ++t;
@@ -370,20 +423,20 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     // whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
-    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN);
     const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem_a));
     const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem_b));
     // The loop body is kept minimal (ring position kept incrementally, parameters hoisted, no trace code unless
     // built with CGS_TRACE): the issuing thread runs in lock-step with the tensor pipe, so every instruction here is
     // a bubble between K blocks.  Releasing a stage one K block late (commit after the next block's MMAs) was
     // measured and is slower: ring depth (3-4 stages) matters more than the issue bubble.
-    if (elect_one()) {                         // one thread walks the whole loop
+    if (elect_one() && leader) {               // one thread (of the pair's leader) walks the whole loop
     uint32_t it_global = 0;
     uint32_t tile_count = 0;
     uint32_t stage = 0, phase = 0;               // position in the smem ring
     const bool a_tma = p.a_tma != 0;
     const bool skip_mma = (p.debug & 4) != 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++tile_count) {
       const int ci = fast_div(tile, fd_tpc);
       const uint32_t acc = tile_count % C::NACC;
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
@@ -407,16 +460,16 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
                 // one MMA of N = run_len * BN columns per k-step: adjacent class slots = adjacent TMEM columns and
                 // adjacent weight atoms in the stage, the A tile is read once for all of them
                 const uint32_t slot = sh.run_slot[r];
-                const uint32_t idesc_r = make_idesc_tf32(BM, BN * sh.run_len[r]);
+                const uint32_t idesc_r = make_idesc_tf32(BM * CG, BN * sh.run_len[r]);
                 const uint32_t had = (cb > 0) ? 1u : sh.run_acc[r];
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k)
-                  umma_tf32_ss(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc_r,
-                               (had || k > 0) ? 1u : 0u);
+                  umma<CG>(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc_r,
+                           (had || k > 0) ? 1u : 0u);
               }
             }
-            umma_commit(&empty_bar[s]);
-            if (last) umma_commit(&tmem_full_bar[acc]);
+            commit<CG>(&empty_bar[s]);
+            if (last) commit<CG>(&tmem_full_bar[acc]);
             trace(p, 2, 1, it_global);
           }
         }
@@ -442,8 +495,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             if (a >= na) break;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_ss(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
-                           (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
+              umma<CG>(tmem_d, da + a * (A_ATOM_BYTES >> 4) + 2 * k, db + a * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc,
+                       (kb > 0 || a > 0 || k > 0) ? 1u : 0u);
             if (PAIR) {                        // second M tile of the pair: its own A atom, the SAME weight atom
 #pragma unroll
               for (int k = 0; k < BK / 8; ++k)
@@ -451,8 +504,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             }
           }
         }
-        umma_commit(&empty_bar[s]);                            // smem stage reusable once these MMAs have read it
-        if (last) umma_commit(&tmem_full_bar[acc]);            // accumulator complete
+        commit<CG>(&empty_bar[s]);                             // smem stage reusable once these MMAs have read it
+        if (last) commit<CG>(&tmem_full_bar[acc]);             // accumulator complete
         trace(p, 2, 1, it_global);
       }
     }
@@ -493,7 +546,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       l_pos[ps] = r < p.rows_valid ? (multi_img ? bb : hh) : (1 << 28);   // padding rows never pass the bound test
     }
     for (uint32_t tile_count = kSplitTiles ? group : 0;; tile_count += tile_groups) {
-      const int tile = blockIdx.x + tile_count * gridDim.x;
+      const int tile = tile_first + (int)tile_count * tile_stride;
       if (tile >= total_tiles) break;
       const int ci = fast_div(tile, fd_tpc);
       const int rem = tile - ci * tiles_per_class;
@@ -508,7 +561,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       for (int slot = 0; slot < nslots; ++slot) {
       const int cls_i = FUSED ? p.grp[ci].cls[slot] : ci;
       const bool last_slot = slot == nslots - 1;
-      const int m_tile = PAIR ? 2 * m_unit + slot : m_unit;    // pair mode: slot = which M tile of the pair
+      // M-tile pair: slot = which M tile of the pair; CTA pair: this CTA's tile of the unit
+      const int m_tile = PAIR ? 2 * m_unit + slot : (CG2 ? 2 * m_unit + (int)cta_rank : m_unit);
+      const bool tile_live = !CG2 || m_tile < m_tiles_live;    // the odd tile of the last CTA pair may not exist
       const int mb = fast_div(m_tile, p.fd_hy_tiles);
       const int b0 = mb * p.BB;
       const int j0 = (m_tile - mb * p.hy_tiles) * p.BH;
@@ -518,7 +573,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       int ro[PASSES];                              // element offset of each stored row in out / aux / mom, -1 = none
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps)
-        ro[ps] = ((multi_img ? b0 : j0) + l_pos[ps] < lim) ? t_off + l_off[ps] : -1;
+        ro[ps] = (tile_live && (multi_img ? b0 : j0) + l_pos[ps] < lim) ? t_off + l_off[ps] : -1;
       // chunks of this tile that hold valid output channels (ON is a multiple of 4; the tail of the last n tile and
       // the zero columns of a narrow N are never read out of TMEM)
       const int n0 = n_tile * BN;
@@ -566,7 +621,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           if (last_slot) {
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+              if (CG2 && !leader) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+            }
             if (warp == 0 && lane == 0) trace(p, 3, 1, tile_count);
           }
           released = true;
@@ -610,7 +667,10 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (CG2) cluster_sync_all();                   // the leader's MMAs write this CTA's TMEM and barriers until its last commit
+  if (warp == kMmaWarp) {
+    if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -801,6 +861,19 @@ void build_fusion(ConvGemmParams& p, int NS) {
         i += len;
       }
       for (int i = 0; i < sh.ncls; ++i) touched |= 1u << sh.slot[i];
+      for (int rank = 0; rank < 2; ++rank) {
+        int n = 0, e0 = 0;
+        for (int r = 0; r < sh.nrun; ++r) {
+          const int L = sh.run_len[r];
+          for (int j = 0; j < L; ++j, ++n) {
+            const int g = rank * L + j;               // half-atom piece of the run's 2 L
+            sh.pc_slot[rank][n] = (unsigned char)(sh.run_slot[r] + j);
+            sh.pc_half[rank][n] = (unsigned char)(g & 1);
+            sh.pc_katom[rank][n] = sh.katom0[e0 + (g >> 1)];
+          }
+          e0 += L;
+        }
+      }
       p.shf[nshf++] = sh;
     }
     G.nshifts = nshf - G.shift0;
@@ -826,16 +899,16 @@ int fusion_slots(const ConvGemmParams& p, int bn) {
   return 0;
 }
 
-template <int BN, int EPI, int NS = 1, int MT = 1>
+template <int BN, int EPI, int NS = 1, int MT = 1, int CG = 1>
 int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
-  using C = Cfg<BN, NS, MT>;
+  using C = Cfg<BN, NS, MT, CG>;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
   // weights [rows][K] viewed as {32 (k inside an atom), rows, K/32 (atom)}: a box {32, BN, KB} lands as KB atom tiles
   cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)w_rows, (cuuint64_t)(w_cols / BK)};
   cuuint64_t gstride[2] = {(cuuint64_t)w_cols * sizeof(float), (cuuint64_t)BK * sizeof(float)};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, (cuuint32_t)C::KB};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / CG), (cuuint32_t)C::KB};   // CTA pair: half an atom per box
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -890,34 +963,46 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
   const int num_sms = device_num_sms();
   {
     static DynSmemCache smem_cache;            // per kernel instantiation, per device
-    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS, MT>, (size_t)C::SMEM_BYTES, smem_cache);
+    cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS, MT, CG>, (size_t)C::SMEM_BYTES, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   if (NS > 1) build_fusion(p, NS); else p.fuse = 0;
-  p.m2 = MT > 1;
-  const int m_units = MT > 1 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  p.m2 = MT > 1 || CG > 1;                    // the scheduling unit is two adjacent M tiles
+  const int m_units = p.m2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const long long total_ll = (long long)m_units * p.n_tiles * (NS > 1 ? p.ngroups : p.nclasses);
   if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
   const int total = (int)total_ll;
   p.fd_tiles_per_class = fast_div_magic((unsigned)(m_units * p.n_tiles));
   p.fd_n_tiles = fast_div_magic((unsigned)p.n_tiles);
   p.fd_hy_tiles = fast_div_magic((unsigned)p.hy_tiles);
-  const int grid = total < num_sms ? total : num_sms;
-  cudaError_t e = launch_pdl(conv_gemm_tc_kernel<BN, EPI, NS, MT>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, p, tmap, tmap_a);
+  // CTA pairs: one cluster of two per unit, at most one CTA per SM (148 = 2 x 74 TPCs)
+  const int grid = CG > 1 ? (2 * total < (num_sms & ~1) ? 2 * total : (num_sms & ~1)) : (total < num_sms ? total : num_sms);
+  cudaError_t e = launch_pdl_cluster(conv_gemm_tc_kernel<BN, EPI, NS, MT, CG>, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES,
+                                     stream, CG, p, tmap, tmap_a);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "conv_gemm_tc launch: %s", cudaGetErrorString(e));
   return CGS_OK;
 }
 
-template <int BN, int NS = 1, int MT = 1>
+template <int BN, int NS = 1, int MT = 1, int CG = 1>
 int launch_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   switch (p.epi) {                          // the epilogue mode is compiled into the kernel
-    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD, NS, MT>(p, w, w_rows, w_cols, stream);
-    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD, NS, MT>(p, w, w_rows, w_cols, stream);
-    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE, NS, MT>(p, w, w_rows, w_cols, stream);
-    default: return launch_tc_epi<BN, EPI_RAW, NS, MT>(p, w, w_rows, w_cols, stream);
+    case EPI_FWD: return launch_tc_epi<BN, EPI_FWD, NS, MT, CG>(p, w, w_rows, w_cols, stream);
+    case EPI_BWD: return launch_tc_epi<BN, EPI_BWD, NS, MT, CG>(p, w, w_rows, w_cols, stream);
+    case EPI_UPDATE: return launch_tc_epi<BN, EPI_UPDATE, NS, MT, CG>(p, w, w_rows, w_cols, stream);
+    default: return launch_tc_epi<BN, EPI_RAW, NS, MT, CG>(p, w, w_rows, w_cols, stream);
   }
+}
+
+// CTA pairs (cta_group::2) are taken for the passes whose stages are widest in bytes per MMA cycle -- class-fused tiles
+// and 256-wide tiles -- when the TMA'd A operand is in use and every SM still gets a tile.  CGS_DEBUG bit 16777216
+// switches them off, 33554432 forces them whenever legal (parity tests at small batch).
+bool use_cta_pairs(const ConvGemmParams& p, long long units_total, int num_sms) {
+  if (debug_flags() & (16777216 | 512)) return false;
+  if (p.cblocks <= 0 || p.window) return false;
+  if (debug_flags() & 33554432) return true;
+  return 2 * units_total >= (num_sms & ~1);
 }
 
 void derive_act(ConvGemmParams& p) {
@@ -967,10 +1052,11 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     const int bn_full = pick_bn(p.N);
     const int ns = fusion_slots(p, bn_full);
     if (ns && ((debug_flags() & 1048576) || count_m_tiles(p) * (ns == 2 ? 2 : 1) >= num_sms)) {
+      const bool pairs = use_cta_pairs(p, (long long)((count_m_tiles(p) + 1) / 2) * (ns == 2 ? 2 : 1), num_sms);
       switch (ns * 1000 + bn_full) {
         case 4032: return launch_tc<32, 4>(p, w, w_rows, w_cols, stream);
-        case 4064: return launch_tc<64, 4>(p, w, w_rows, w_cols, stream);
-        case 2128: return launch_tc<128, 2>(p, w, w_rows, w_cols, stream);
+        case 4064: return pairs ? launch_tc<64, 4, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<64, 4>(p, w, w_rows, w_cols, stream);
+        case 2128: return pairs ? launch_tc<128, 2, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 2>(p, w, w_rows, w_cols, stream);
         default: break;
       }
     }
@@ -994,7 +1080,10 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     case 32: return launch_tc<32>(p, w, w_rows, w_cols, stream);
     case 64: return launch_tc<64>(p, w, w_rows, w_cols, stream);
     case 128: return launch_tc<128>(p, w, w_rows, w_cols, stream);
-    default: return launch_tc<256>(p, w, w_rows, w_cols, stream);
+    default:
+      if (use_cta_pairs(p, (long long)((count_m_tiles(p) + 1) / 2) * ((p.N + 255) / 256) * p.nclasses, num_sms))
+        return launch_tc<256, 1, 1, 2>(p, w, w_rows, w_cols, stream);
+      return launch_tc<256>(p, w, w_rows, w_cols, stream);
   }
 }
 

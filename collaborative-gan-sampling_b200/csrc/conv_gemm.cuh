@@ -41,6 +41,10 @@ struct FuseShift {
   // cycles of tensor work); run_acc = the slots already hold partial sums
   unsigned char nrun, run_slot[4], run_len[4], run_acc[4];
   int katom0[4];                // first K atom (32 floats) of that tap's weights; + channel block
+  // CTA pairs: a run's B rows are its atoms back to back, split in the middle between the two CTAs.  Per CTA rank the
+  // half-atom boxes to fetch: destination slot (half an atom wide per CTA), which half of the atom, its K atom
+  unsigned char pc_slot[2][4], pc_half[2][4];
+  int pc_katom[2][4];
 };
 struct FuseGroup {
   int nshifts, shift0, ncls;    // shifts [shift0, shift0 + nshifts) of shf[]; classes in this group

@@ -111,6 +111,35 @@ def test_m_tile_pairs_are_bit_identical(cgs_lib, cuda_device, arch_name, B, gain
     assert all(torch.equal(a, b) for a, b in zip(default, single))
 
 
+@pytest.mark.parametrize("arch_name,B,gain", [("dcgan32_l2", 7, 2.5), ("dcgan64_l1", 3, 2.5), ("dcgan64_l3", 5, 2.5),
+                                               ("dcgan32_l1", 1024, 2.5), ("dcgan32_l2", 601, 2.5)])
+def test_cta_pairs_are_bit_identical(cgs_lib, cuda_device, arch_name, B, gain):
+    """CTA pairs (cluster of two, tcgen05 cta_group::2, M = 256; CGS_DEBUG 33554432 forces them, 16777216 forbids them):
+    every accumulator row sees the same K order as in a single-CTA tile, so the results are bit-identical -- with
+    class-fused tiles and 256-wide tiles, odd tile counts (the pair's second tile past the batch) and several units per
+    pair."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 5, gain, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(4))).to(cuda_device)
+
+    def run(flags):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(3, 0.1)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            x = r.build_refiner(h0)
+            torch.cuda.synchronize()
+            return x.clone(), r.optimal_logit.clone(), r.current_feature.clone()
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    paired, single = run(33554432 | 1048576), run(16777216 | 1048576)   # class fusion forced in both
+    assert all(torch.equal(a, b) for a, b in zip(paired, single))
+    default = run(0)
+    assert all(torch.equal(a, b) for a, b in zip(default, single))
+
+
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 @pytest.mark.parametrize("arch_name,B", [("mnist", 5), ("mnist", 67), ("dcgan32_l1", 3), ("dcgan64_l2", 2), ("dcgan64_l2", 9)])
 def test_layers_forward_backward(cgs_lib, cuda_device, arch_name, B, math):

@@ -9,9 +9,12 @@ from cgs import lib as L, nets as N, synthetic as S
 from sampling.collaborator import Refiner
 
 lib = L.load()
-lib.cgs_debug_set_flags(1048576)          # class-fused tiles whenever legal
 dev = torch.device("cuda", 0)
-for name, B, thr in (("dcgan64_l1", 5, None), ("dcgan32_l2", 6, None), ("dcgan64_l3", 3, 0.0), ("mnist", 20, 0.1)):
+# default rules / class-fused tiles whenever legal / class fusion + M-tile pairs whenever legal
+for flags, name, B, thr in ((0, "dcgan64_l1", 5, None), (1048576, "dcgan64_l1", 5, None), (1048576, "dcgan32_l2", 6, None),
+                            (1048576 | 8388608, "dcgan64_l3", 3, 0.0), (8388608, "dcgan32_l4", 4, None),
+                            (1048576, "mnist", 20, 0.1)):
+    lib.cgs_debug_set_flags(flags)
     arch = N.get_arch(name)
     spec = N.NetSpec(arch, S.init_weights(arch, gain=3.0 if name == "mnist" else 2.5), dev)
     r = Refiner(3, 0.1)
@@ -20,5 +23,5 @@ for name, B, thr in (("dcgan64_l1", 5, None), ("dcgan32_l2", 6, None), ("dcgan64
     h0 = torch.from_numpy(S.proposal_features(arch, B, seed=1)).to(dev)
     x = r.build_refiner(h0)
     torch.cuda.synchronize()
-    print(name, "ok", tuple(x.shape), float(r.optimal_logit.mean()))
+    print(flags, name, "ok", tuple(x.shape), float(r.optimal_logit.mean()))
 print("launches", lib.cgs_launch_count())

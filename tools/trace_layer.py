@@ -66,3 +66,26 @@ for key in sorted(names):
     d = np.diff(ts) if len(ts) > 1 else []
     print("%-14s n=%4d first=%7d last=%8d  mean dt=%7.1f  first 40 t: %s" % (names[key], len(ts), ts[0] if ts else -1, ts[-1] if ts else -1,
           float(np.mean(d)) if len(d) else 0.0, ts[:40]))
+# steady-state table: per ring stage the time the weight-TMA thread saw the slot empty, the MMA thread saw it full and
+# committed it (cycles since the first event; dM = commit -> next commit)
+by = {}
+for e in ev:
+    if e[0] in (1, 2):
+        by.setdefault(e[2], {})[(e[0], e[1])] = (e[3] - t0) & 0xffffffff
+lo = int(os.environ.get("TRACE_FROM", "144"))
+print("stage  T.got_empty  M.got_full  M.commit   full-empty  commit-full  commit-prev_commit")
+prev = None
+for k in range(lo, lo + 80):
+    r = by.get(k)
+    if not r:
+        continue
+    te, mf, mc = r.get((1, 0), -1), r.get((2, 0), -1), r.get((2, 1), -1)
+    print("%5d  %10d  %10d  %9d  %9d  %9d  %9s" % (k, te, mf, mc, mf - te, mc - mf, (mc - prev) if prev is not None else "-"))
+    prev = mc
+tiles = {}
+for e in ev:
+    if e[0] == 3:
+        tiles.setdefault(e[2], {})[e[1]] = (e[3] - t0) & 0xffffffff
+print("tile  E.tmem_full  E.released  E.done")
+for k in sorted(tiles)[:16]:
+    print("%4d  %s" % (k, "  ".join("%9d" % tiles[k].get(i, -1) for i in range(3))))
