@@ -446,6 +446,18 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const FuseGroup& G = p.grp[ci];
         for (int si = 0; si < G.nshifts; ++si) {
           const FuseShift& sh = p.shf[G.shift0 + si];
+          // the runs of this shift, decoded once for all channel blocks (the issuing thread is the slowest role of the
+          // stages with one or two classes: 64 - 256 cycles of tensor work against a loop of ~350)
+          const int nrun = sh.nrun;
+          uint32_t r_tm[4], r_db[4], r_idesc[4], r_acc[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t slot = sh.run_slot[r];
+            r_tm[r] = slot * BN;
+            r_db[r] = slot * (C::B_ATOM_BYTES >> 4);
+            r_idesc[r] = make_idesc_tf32(BM * CG, BN * sh.run_len[r]);
+            r_acc[r] = sh.run_acc[r];
+          }
           for (int cb = 0; cb < p.cblocks; ++cb, ++it_global) {
             const uint32_t s = stage;
             const bool last = (si == G.nshifts - 1) && (cb == p.cblocks - 1);
@@ -456,16 +468,15 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             const uint64_t da = da0 + (uint64_t)(s * (C::A_STAGE_BYTES >> 4));
             const uint64_t db = db0 + (uint64_t)(s * (C::B_STAGE_BYTES >> 4));
             if (!skip_mma) {
-              for (int r = 0; r < sh.nrun; ++r) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if (r >= nrun) break;
                 // one MMA of N = run_len * BN columns per k-step: adjacent class slots = adjacent TMEM columns and
                 // adjacent weight atoms in the stage, the A tile is read once for all of them
-                const uint32_t slot = sh.run_slot[r];
-                const uint32_t idesc_r = make_idesc_tf32(BM * CG, BN * sh.run_len[r]);
-                const uint32_t had = (cb > 0) ? 1u : sh.run_acc[r];
+                const uint32_t had = (cb > 0) ? 1u : r_acc[r];
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k)
-                  umma<CG>(tmem_d + slot * BN, da + 2 * k, db + slot * (C::B_ATOM_BYTES >> 4) + 2 * k, idesc_r,
-                           (had || k > 0) ? 1u : 0u);
+                  umma<CG>(tmem_d + r_tm[r], da + 2 * k, db + r_db[r] + 2 * k, r_idesc[r], (had || k > 0) ? 1u : 0u);
               }
             }
             commit<CG>(&empty_bar[s]);
