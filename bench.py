@@ -356,7 +356,7 @@ def build_roofline(torch, spec, arch, arch_name, batch, math, dev, ksteps, step_
     }
     if edge:
         b_edge = sum(r["bytes"] for r in edge)
-        roof["edge"] = {"bound": "hbm", "kernel": "image-edge passes (mma.sync TF32 streaming kernels, csrc/edge_conv.cu)",
+        roof["edge"] = {"bound": "hbm", "kernel": "image-edge passes (tcgen05 resident-patch kernels on the space-to-depth image, csrc/edge_tc.cu; mma.sync streaming kernels of csrc/edge_conv.cu on maps narrower than 16)",
                         "achieved": round(b_edge / t_edge / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(b_edge / t_edge / 1e9 / hbm_peak, 4), "peak_source": src + " hbm_gbs",
                         "algorithmic_bytes_per_launch_set": int(b_edge), "us": round(t_edge * 1e6, 1),

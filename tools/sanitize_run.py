@@ -10,9 +10,10 @@ from sampling.collaborator import Refiner
 
 lib = L.load()
 dev = torch.device("cuda", 0)
-# default rules / class-fused tiles whenever legal / class fusion + M-tile pairs whenever legal
+# default rules / class-fused tiles whenever legal / class fusion + M-tile pairs / CTA pairs (cta_group::2) whenever legal
 for flags, name, B, thr in ((0, "dcgan64_l1", 5, None), (1048576, "dcgan64_l1", 5, None), (1048576, "dcgan32_l2", 6, None),
                             (1048576 | 8388608, "dcgan64_l3", 3, 0.0), (8388608, "dcgan32_l4", 4, None),
+                            (1048576 | 33554432, "dcgan64_l1", 5, None), (33554432, "dcgan32_l2", 7, 0.0),
                             (1048576, "mnist", 20, 0.1)):
     lib.cgs_debug_set_flags(flags)
     arch = N.get_arch(name)
