@@ -529,14 +529,15 @@ def measure_2d(torch, dev, n=10000, steps_k=50, reps=5, cpu=True):
     out = {"value": n / best, "unit": "refined points/s", "ms_per_pass": best * 1e3,
            "workload": "2-D MLP D (2-64x5-1), N=%d, ladam K=%d, then DRS(p=100) and MH(T=20)" % (n, steps_k),
            "mflop_per_point": round(flop_point / 1e6, 3),
-           "roofline": {"bound": "fp32_fma", "kernel": "mlp2d_refine_kernel (one launch for all K steps)",
+           "roofline": {"bound": "fp32_fma", "kernel": "mlp2d_refine_split_kernel (one launch for all K steps, four threads per point)",
                         "achieved": round(n * flop_point / best_refine / 1e12, 2), "peak": round(fma_peak, 1),
                         "unit": "TFLOP/s", "frac": round(n * flop_point / best_refine / 1e12 / fma_peak, 4),
                         "us": round(best_refine * 1e6, 1),
                         "peak_source": "%d SMs x 128 FP32 lanes x 2 x %.3f GHz (device max clock); weights are "
                                        "shared-memory resident, only x in / x out touch HBM" % (props.multi_processor_count, clk_ghz),
-                        "note": "N = 10^4 points is %d warps on %d SMs: the launch cannot fill the machine"
-                                % ((n + 31) // 32, props.multi_processor_count)}}
+                        "note": "N = 10^4 points is %d point-warps on %d SMs; bound by the shared-memory pipe (warp-broadcast "
+                                        "LDS.128 weight reads, 4 FMAs per load: 69 %% of peak wavefronts in ncu, "
+                                        "profiles/round2_ncu_summary.md E)" % ((n + 31) // 32, props.multi_processor_count)}}
     if cpu:
         from oracle import nets as onets
         from oracle import sampling_np as snp

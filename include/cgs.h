@@ -254,7 +254,8 @@ CGS_API int cgs_debug_trace_tc(long long* out_host);
  * paired ones; 16384 disables split-K on the long fc forward; 32768 adds programmatic dependent launch; 262144
  * keeps the column-buffer form of the narrow edge kernel; 524288 disables / 1048576 forces the class-fused tcgen05
  * tiles of the transposed-type passes; 4194304 disables / 8388608 forces M-tile pairs; 16777216 disables / 33554432
- * forces CTA pairs (clusters of two, tcgen05 cta_group::2). */
+ * forces CTA pairs (clusters of two, tcgen05 cta_group::2); 134217728 runs the 2-D refinement with one thread per
+ * point instead of the four-thread split form (bit-identical). */
 CGS_API int cgs_debug_set_flags(int flags);
 
 #ifdef __cplusplus

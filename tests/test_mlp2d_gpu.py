@@ -81,3 +81,37 @@ def test_probabilistic_returns_float64_trajectory_rows(cgs_lib, cuda_device):
     assert np.abs(out - o["probabilistic"]).max() <= 1e-4 * SCALE
     with pytest.raises(NotImplementedError):
         ref.manipulate_sample(x0, "greedy")
+
+
+@pytest.mark.parametrize("method,K,n,nlayers", [("ladam", 50, 10000, 6), ("momentum", 7, 97, 6), ("sgd", 3, 1, 3),
+                                                ("ladam", 5, 20001, 2), ("ladam", 4, 300, 8)])
+def test_split_refine_kernel_is_bit_identical(cgs_lib, cuda_device, method, K, n, nlayers):
+    """The split form (four threads per point, 16-wide layer slices exchanged through shared memory) accumulates every
+    element in the order of the one-thread form (CGS_DEBUG bit 134217728 selects the latter): same bits for the best
+    point, its loss and step, and the whole trajectory -- at the benchmark size, ragged sizes, a single point, more
+    than 96 points per CTA round, the shallowest and the deepest MLP."""
+    from sampling.refiner_cpu import MlpSpec, Refiner
+    ws = onets.init_mlp2d(64, nlayers, seed=7, gain=1.5)
+    mlp = MlpSpec(ws, cuda_device)
+    rng = np.random.RandomState(2)
+    x0 = (rng.randn(n, 2) * 4).astype(np.float32)
+    real = (rng.randn(max(n, 8), 2) * 3).astype(np.float32)
+    rate = 0.1 if method == "ladam" else 50.0
+
+    def run(flags):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            ref = Refiner(types.SimpleNamespace(rollout_steps=K, rollout_rate=rate, rollout_method=method))
+            ref.set_env(mlp, None, _Data(real))
+            np.random.seed(3)
+            det = ref.manipulate_sample(x0, "deterministic")
+            step, loss = ref.optimal_step.cpu().numpy().copy(), ref.optimal_loss.cpu().numpy().copy()
+            np.random.seed(3)
+            prob = ref.manipulate_sample(x0, "probabilistic")          # reads the full trajectory
+            return det, step, loss, prob
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    a, b = run(0), run(134217728)
+    for u, v in zip(a, b):
+        assert np.array_equal(np.asarray(u), np.asarray(v))
