@@ -90,7 +90,7 @@ struct Cfg {
   static constexpr int ACC_COLS = NS * MT * BN;
   static constexpr int NACC = (NS > 1 || MT > 1) ? 512 / ACC_COLS : ((BN >= 256) ? 2 : 4);
   static_assert(NS == 1 || MT == 1, "class fusion and M-tile pairs are separate modes");
-  static_assert(CG == 1 || (CG == 2 && MT == 1), "CTA pairs replace M-tile pairs");
+  static_assert(CG == 1 || CG == 2, "clusters of one or two CTAs");
   static_assert(MT == 1 || (MT == 2 && BN <= 128), "M-tile pairs need 2 * BN TMEM columns per buffer, two buffers");
   static constexpr int TMEM_COLS = NACC * ACC_COLS;
   static_assert(NS == 1 || (ACC_COLS <= 256 && BN <= 128), "fused tiles need two TMEM buffers");
@@ -371,13 +371,18 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             const int mbA = fast_div(mt0, p.fd_hy_tiles), mbB = fast_div(mt0 + 1, p.fd_hy_tiles);
             const int b0A = mbA * p.BB, yA = (mt0 - mbA * p.hy_tiles) * p.BH * p.S;
             const int b0B = mbB * p.BB, yB = (mt0 + 1 - mbB * p.hy_tiles) * p.BH * p.S;
-            const bool second = mt0 + 1 < m_tiles_live;
+            const bool second = CG2 || mt0 + 1 < m_tiles_live;   // (CTA pairs: always both, a box past the batch reads zeros)
             for (int kb = 0; kb < nkb; ++kb) {
               const uint32_t s = stage, ph = phase;
               if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
               mbar_wait(&empty_bar[s], ph ^ 1);
               if (skip) {
-                mbar_arrive(&full_bar[s]);
+                if (leader) mbar_arrive(&full_bar[s]);
+              } else if (CG2) {
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], 4u * a_bytes);
+                tma_load_4d_cg2(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], (cb + cb0) * BK, gc.dx[t], yA + gc.dy[t], b0A);
+                tma_load_4d_cg2(smem_a_u32 + s * C::A_STAGE_BYTES + A_ATOM_BYTES, &tmap_a, &full_bar[s], (cb + cb0) * BK, gc.dx[t],
+                                yB + gc.dy[t], b0B);
               } else {
                 mbar_arrive_expect_tx(&full_bar[s], second ? 2u * a_bytes : a_bytes);
                 tma_load_4d(smem_a_u32 + s * C::A_STAGE_BYTES, &tmap_a, &full_bar[s], (cb + cb0) * BK, gc.dx[t], yA + gc.dy[t], b0A);
@@ -511,7 +516,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             if (PAIR) {                        // second M tile of the pair: its own A atom, the SAME weight atom
 #pragma unroll
               for (int k = 0; k < BK / 8; ++k)
-                umma_tf32_ss(tmem_d + BN, da + (A_ATOM_BYTES >> 4) + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma<CG>(tmem_d + BN, da + (A_ATOM_BYTES >> 4) + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
         }
@@ -567,13 +572,14 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       const uint32_t acc_ph = (tile_count / C::NACC) & 1;
       // a fused tile holds one accumulator per class of its group (slots): the same epilogue runs once per slot with
       // that class's output offsets; the TMEM buffer goes back to the MMA warp after the last slot has been read
-      const int nslots = FUSED ? p.grp[ci].ncls : (PAIR ? (2 * m_unit + 1 < m_tiles_live ? 2 : 1) : 1);
+      const int nslots = FUSED ? p.grp[ci].ncls : (PAIR ? ((CG2 || 2 * m_unit + 1 < m_tiles_live) ? 2 : 1) : 1);
       bool waited = false;
       for (int slot = 0; slot < nslots; ++slot) {
       const int cls_i = FUSED ? p.grp[ci].cls[slot] : ci;
       const bool last_slot = slot == nslots - 1;
       // M-tile pair: slot = which M tile of the pair; CTA pair: this CTA's tile of the unit
-      const int m_tile = PAIR ? 2 * m_unit + slot : (CG2 ? 2 * m_unit + (int)cta_rank : m_unit);
+      const int m_tile = PAIR ? (CG2 ? 4 * m_unit + 2 * (int)cta_rank + slot : 2 * m_unit + slot)
+                              : (CG2 ? 2 * m_unit + (int)cta_rank : m_unit);
       const bool tile_live = !CG2 || m_tile < m_tiles_live;    // the odd tile of the last CTA pair may not exist
       const int mb = fast_div(m_tile, p.fd_hy_tiles);
       const int b0 = mb * p.BB;
@@ -978,8 +984,8 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   if (NS > 1) build_fusion(p, NS); else p.fuse = 0;
-  p.m2 = MT > 1 || CG > 1;                    // the scheduling unit is two adjacent M tiles
-  const int m_units = p.m2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  p.m2 = MT * CG;                             // adjacent M tiles per scheduling unit
+  const int m_units = (p.m_tiles + p.m2 - 1) / p.m2;
   const long long total_ll = (long long)m_units * p.n_tiles * (NS > 1 ? p.ngroups : p.nclasses);
   if (total_ll >= (1ll << 31)) return set_error(CGS_ERR_UNSUPPORTED, "tile count exceeds 2^31");
   const int total = (int)total_ll;
@@ -1083,8 +1089,13 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
     // whole rounds over the SMs: a pair round costs two tile rounds at 0.78x / 0.85x of their bytes
     const double cost_pair = (double)((pairs + num_sms - 1) / num_sms) * 2.0 * (bn == 128 ? 0.78 : 0.85);
     const double cost_single = (double)((tiles + num_sms - 1) / num_sms);
-    if ((debug_flags() & 8388608) || (pairs >= num_sms && cost_pair < cost_single))
+    if ((debug_flags() & 8388608) || (pairs >= num_sms && cost_pair < cost_single)) {
+      // M-tile pairs inside CTA pairs (four M tiles share each weight atom, half of it per CTA): 40 KB instead of
+      // 48 KB of L2 -> SM traffic per 512 tensor cycles on passes that sit at the L2 throughput ceiling
+      if (bn == 128 && use_cta_pairs(p, (long long)((count_m_tiles(p) + 3) / 4) * nt, num_sms))
+        return launch_tc<128, 1, 2, 2>(p, w, w_rows, w_cols, stream);
       return bn == 64 ? launch_tc<64, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 1, 2>(p, w, w_rows, w_cols, stream);
+    }
   }
   switch (bn) {
     case 16: return launch_tc<16>(p, w, w_rows, w_cols, stream);

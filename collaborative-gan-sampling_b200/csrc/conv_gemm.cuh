@@ -98,7 +98,8 @@ struct ConvGemmParams {
   const int* live;
   // class fusion (see FuseShift): 0 = one class per tile, else the launcher filled grp / shf
   int fuse, ngroups;
-  // two M tiles per CTA tile (conv_gemm.cu, template MT = 2): the pair shares every weight atom of its K loop
+  // adjacent M tiles per scheduling unit: 2 with M-tile pairs (template MT = 2: the pair shares every weight atom
+  // of its K loop) or CTA pairs (CG = 2: one tile per CTA of the cluster), 4 with both, else 1 (0 reads as 1)
   int m2;
   FuseGroup grp[2];
   FuseShift shf[kMaxShifts];
@@ -143,14 +144,14 @@ __device__ __forceinline__ LiveTiles live_tiles(const ConvGemmParams& p) {
   LiveTiles t;
   if (!p.live) {
     t.B = p.B;
-    t.tiles_per_class = (p.m2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+    t.tiles_per_class = (p.m2 > 1 ? (p.m_tiles + p.m2 - 1) / p.m2 : p.m_tiles) * p.n_tiles;
     t.fd_tiles_per_class = p.fd_tiles_per_class;
   } else {
     int b = *reinterpret_cast<const volatile int*>(p.live);
     b = b < 0 ? 0 : (b > p.B ? p.B : b);
     t.B = b;
     const int mt_live = ((b + p.BB - 1) / p.BB) * p.hy_tiles;
-    t.tiles_per_class = (p.m2 ? (mt_live + 1) / 2 : mt_live) * p.n_tiles;
+    t.tiles_per_class = (p.m2 > 1 ? (mt_live + p.m2 - 1) / p.m2 : mt_live) * p.n_tiles;
     t.fd_tiles_per_class = fast_div_magic_dev((unsigned)t.tiles_per_class);
   }
   t.total = t.tiles_per_class * (p.fuse ? p.ngroups : p.nclasses);

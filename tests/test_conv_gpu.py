@@ -138,6 +138,9 @@ def test_cta_pairs_are_bit_identical(cgs_lib, cuda_device, arch_name, B, gain):
     assert all(torch.equal(a, b) for a, b in zip(paired, single))
     default = run(0)
     assert all(torch.equal(a, b) for a, b in zip(default, single))
+    # M-tile pairs INSIDE CTA pairs (units of four M tiles; class fusion off so the 128-wide passes take them)
+    quad = run(33554432 | 8388608 | 524288)
+    assert all(torch.equal(a, b) for a, b in zip(quad, single))
 
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
