@@ -31,7 +31,8 @@ def test_sass_is_blackwell_native():
     so = os.path.join(ROOT, "collaborative-gan-sampling_b200", "cgs", "libcgs.so")
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100" in sass.upper()
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+    # tcgen05 MMAs / TMA loads / TMEM loads / commits, and the CTA-pair (cta_group::2) forms with multicast commits
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UTCHMMA.2CTA", "UTMALDG.4D.2CTA", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in sass, mnemonic
 
 
