@@ -1081,20 +1081,24 @@ int launch_conv_gemm_tc(const ConvGemmParams& p_in, const float* w, int w_rows, 
   // M-tile pairs sharing the weight atoms (MT = 2): 64- / 128-wide one-class tiles with a TMA'd A operand, when the
   // pairs still give every SM a tile.  Bit-identical to single tiles (each accumulator sees the same MMA sequence).
   // CGS_DEBUG bit 4194304 switches them off, 8388608 forces them whenever legal.
-  // (64-wide pairs save only 17 % of the bytes and measured slower on the MNIST nets: taken only when forced)
-  if (!p.force_bn && (bn == 128 || (bn == 64 && (debug_flags() & 8388608))) && p.cblocks > 0 && !p.window &&
-      !(debug_flags() & (4194304 | 512)) && p.N > bn / 2) {
+  // (64-wide pairs on one CTA save only 17 % of the bytes and measured slower on the MNIST nets; inside CTA pairs --
+  //  four M tiles per weight atom, half of it per CTA -- they save 25 % and measured 3-7 % faster: taken only there)
+  if (!p.force_bn && (bn == 128 || bn == 64) && p.cblocks > 0 && !p.window && !(debug_flags() & (4194304 | 512)) &&
+      p.N > bn / 2) {
     const long long nt = (long long)((p.N + bn - 1) / bn) * p.nclasses;
     const long long tiles = (long long)count_m_tiles(p) * nt, pairs = (long long)((count_m_tiles(p) + 1) / 2) * nt;
+    const long long quads = (long long)((count_m_tiles(p) + 3) / 4) * nt;
     // whole rounds over the SMs: a pair round costs two tile rounds at 0.78x / 0.85x of their bytes
     const double cost_pair = (double)((pairs + num_sms - 1) / num_sms) * 2.0 * (bn == 128 ? 0.78 : 0.85);
     const double cost_single = (double)((tiles + num_sms - 1) / num_sms);
-    if ((debug_flags() & 8388608) || (pairs >= num_sms && cost_pair < cost_single)) {
-      // M-tile pairs inside CTA pairs (four M tiles share each weight atom, half of it per CTA): 40 KB instead of
-      // 48 KB of L2 -> SM traffic per 512 tensor cycles on passes that sit at the L2 throughput ceiling
-      if (bn == 128 && use_cta_pairs(p, (long long)((count_m_tiles(p) + 3) / 4) * nt, num_sms))
-        return launch_tc<128, 1, 2, 2>(p, w, w_rows, w_cols, stream);
-      return bn == 64 ? launch_tc<64, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 1, 2>(p, w, w_rows, w_cols, stream);
+    const bool forced = (debug_flags() & 8388608) != 0;
+    if (forced || (pairs >= num_sms && cost_pair < cost_single)) {
+      // M-tile pairs inside CTA pairs: 40 KB instead of 48 KB of L2 -> SM traffic per 512 tensor cycles (BN = 128) on
+      // passes that sit at the L2 throughput ceiling
+      if (use_cta_pairs(p, quads, num_sms))
+        return bn == 64 ? launch_tc<64, 1, 2, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 1, 2, 2>(p, w, w_rows, w_cols, stream);
+      if (bn == 128 || forced)
+        return bn == 64 ? launch_tc<64, 1, 2>(p, w, w_rows, w_cols, stream) : launch_tc<128, 1, 2>(p, w, w_rows, w_cols, stream);
     }
   }
   switch (bn) {
