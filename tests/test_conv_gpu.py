@@ -394,3 +394,39 @@ def test_early_exit_compaction_matches_oracle(cgs_lib, cuda_device, arch_name, B
     b = ref.build_refiner(h0.to(cuda_device))
     assert torch.equal(a, b) and torch.equal(plain.optimal_logit, ref.optimal_logit)
     assert torch.equal(plain.current_feature, ref.current_feature)
+
+
+@pytest.mark.parametrize("arch_name,B,K", [("dcgan32_l2", 37, 5), ("dcgan64_l2", 11, 4)])
+def test_early_exit_is_identical_across_tile_lowerings(cgs_lib, cuda_device, arch_name, B, K):
+    """Device-side early exit under every tcgen05 tile lowering (TF32 mode): class-fused tiles, M-tile pairs, CTA pairs
+    and M-tile pairs inside CTA pairs all read the live-image count and schedule tiles from it; units whose second /
+    third / fourth M tile lies past the live images must neither be stored nor disturb the others.  Same bits as the
+    plain one-tile-per-CTA lowering, eager and replayed as a CUDA graph."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make(arch_name, 9, 2.5, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(B, *arch["feature_shape"], generator=torch.Generator().manual_seed(6))).to(cuda_device)
+    probe = Refiner(K // 2, 0.1)
+    probe.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+    probe.build_refiner(h0)
+    thr = float(torch.median(probe.optimal_logit))            # about half of the batch has left by step K / 2
+
+    def run(flags, graph):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(K, 0.1, cuda_graph=graph)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            r.early_exit_logit = thr
+            x = r.build_refiner(h0, keep_optimal_feature=True)
+            torch.cuda.synchronize()
+            return x.clone(), r.optimal_logit.clone(), r.current_feature.clone(), r.optimal_step.clone(), r.optimal_feature.clone()
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    plain = run(524288 | 4194304 | 16777216, False)           # no fusion, no M-tile pairs, no CTA pairs
+    steps = plain[3].cpu().numpy()
+    assert 0 < (steps < K).sum()                               # some samples did stop early
+    for flags in (1048576, 8388608 | 524288, 33554432 | 1048576, 33554432 | 8388608 | 524288, 0):
+        for graph in (False, True):
+            got = run(flags, graph)
+            assert all(torch.equal(a, b) for a, b in zip(got, plain)), (flags, graph)
