@@ -27,6 +27,15 @@ int debug_flags() {
 }
 void set_debug_flags(int v) { g_debug.store(v < 0 ? 0 : v, std::memory_order_relaxed); }
 
+static thread_local bool tl_pdl = false;
+bool pdl_enabled() {
+  const int f = debug_flags();
+  if (f & 536870912) return false;
+  return tl_pdl || (f & 32768) != 0;
+}
+PdlScope::PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on; }
+PdlScope::~PdlScope() { tl_pdl = prev; }
+
 int current_device() {
   int dev = -1;
   return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;

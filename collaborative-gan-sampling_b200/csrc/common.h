@@ -60,11 +60,19 @@ int debug_flags();
 // Process-wide count of kernels launched by the library (cgs_launch_count).
 void count_launch(int n = 1);
 
-// Launch helper of the chain kernels.  With CGS_DEBUG bit 32768 the launch carries the programmatic stream
+// Launch helper of the chain kernels.  With programmatic dependent launch the launch carries the programmatic stream
 // serialization attribute (the kernels call pdl_wait() before they touch memory written by their predecessor, so a
-// kernel's set-up may overlap the previous kernel's drain).  Measured on B200 inside the replayed CUDA graph it does not
-// pay (19.50 vs 18.92 ms per MNIST step): the per-kernel cost is pipeline ramp and drain, not launch latency, so plain
-// stream order is the default.
+// kernel's set-up -- barrier init, TMEM allocation, tensor-map prefetch -- overlaps the previous kernel's drain).
+// Measured on B200 inside the replayed CUDA graph: +1.5 % on the DCGAN-64 step, +1.1 % on DCGAN-32, -0.8 % on the
+// MNIST-sized nets (their kernels are 20-45 us; an early-resident successor only gets in the way), so the refinement
+// loop switches it on per call from its average work per launch (refine_conv.cu).  CGS_DEBUG bit 32768 forces it on
+// everywhere, 536870912 off.
+bool pdl_enabled();
+struct PdlScope {            // switches programmatic dependent launch on for the launches of the calling thread
+  explicit PdlScope(bool on);
+  ~PdlScope();
+  bool prev;
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -76,7 +84,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (debug_flags() & 32768) ? 1 : 0;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 // Same, as clusters of `cluster_x` CTAs along x (the grid must be a multiple of it).
@@ -97,7 +105,7 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (debug_flags() & 32768) {
+  if (pdl_enabled()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

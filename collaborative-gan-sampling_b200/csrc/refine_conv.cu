@@ -1180,6 +1180,17 @@ extern "C" int cgs_refine_conv(const cgs_net_desc* gtail, const cgs_net_desc* d,
     return set_error(CGS_ERR_UNSUPPORTED, "unknown mode %d", cfg->mode);
   Chain c;
   if (int rc = build_chain(gtail, d, c)) return rc;
+  // programmatic dependent launch for this call's kernels when the average pass is large (common.h launch_pdl):
+  // forward + data-gradient FLOPs of one iteration over its 2 n + 1 launches
+  double macs = 0.0;
+  for (int i = 0; i < c.n; ++i) {
+    const cgs_layer_desc& L = c.layers[i];
+    const double taps = L.type == CGS_LAYER_FC ? 1.0 : (double)L.k * L.k;
+    const double px = L.type == CGS_LAYER_FC ? 1.0 : (L.type == CGS_LAYER_CONV ? (double)((L.hin + 1) / 2) * ((L.win + 1) / 2)
+                                                                              : (double)L.hin * L.win);
+    macs += px * taps * L.cin * L.cout;
+  }
+  const PdlScope pdl_scope(4.0 * macs * (double)B / (2.0 * c.n + 1.0) >= 12e9);     // MNIST B=1024: 7.3 GFLOP (off), DCGAN-32: 18 (on), DCGAN-64: 78 (on)
   Workspace w;
   carve(c, B, (void*)(((uintptr_t)workspace + 255) & ~uintptr_t(255)), w);
   if (!workspace || w.total + 256 > workspace_bytes) return set_error(CGS_ERR_WORKSPACE, "workspace too small");

@@ -251,7 +251,8 @@ CGS_API int cgs_debug_trace_tc(long long* out_host);
  * tests/test_conv_gpu.py).  Bit 4096 routes the image-edge
  * passes (first D conv / last G deconv and their data-gradients) through the general tcgen05 lowerings instead of
  * the fused streaming kernels of csrc/edge_conv.cu; 65536 runs the edge passes as separate kernels instead of the
- * paired ones; 16384 disables split-K on the long fc forward; 32768 adds programmatic dependent launch; 262144
+ * paired ones; 16384 disables split-K on the long fc forward; 32768 forces programmatic dependent launch on everywhere / 536870912 off
+ * (default: per refinement call, from its average work per launch); 262144
  * keeps the column-buffer form of the narrow edge kernel; 524288 disables / 1048576 forces the class-fused tcgen05
  * tiles of the transposed-type passes; 4194304 disables / 8388608 forces M-tile pairs; 16777216 disables / 33554432
  * forces CTA pairs (clusters of two, tcgen05 cta_group::2); 134217728 runs the 2-D refinement with one thread per

@@ -430,3 +430,33 @@ def test_early_exit_is_identical_across_tile_lowerings(cgs_lib, cuda_device, arc
         for graph in (False, True):
             got = run(flags, graph)
             assert all(torch.equal(a, b) for a, b in zip(got, plain)), (flags, graph)
+
+
+def test_programmatic_dependent_launch_is_bit_identical_at_scale(cgs_lib, cuda_device):
+    """At batches where the refinement loop switches programmatic dependent launch on by itself (average pass >= 12
+    GFLOP: DCGAN-64 from 157 rows) the kernels' set-up overlaps the previous kernel's drain; every kernel waits for its
+    predecessor before touching activation memory, so the bits equal those of plain stream order (bit 536870912),
+    eager and replayed as a CUDA graph."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("dcgan64_l1", 5, 2.5, cuda_device, "tf32")
+    h0 = torch.relu(torch.randn(208, *arch["feature_shape"], generator=torch.Generator().manual_seed(8))).to(cuda_device)
+
+    def run(flags, graph):
+        old = cgs_lib.cgs_debug_set_flags(flags)
+        try:
+            r = Refiner(3, 0.1, cuda_graph=graph)
+            r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+            outs = []
+            for _ in range(2):
+                x = r.build_refiner(h0)
+                torch.cuda.synchronize()
+                outs.append((x.clone(), r.optimal_logit.clone(), r.current_feature.clone(), r.optimal_step.clone()))
+            assert all(torch.equal(a, b) for a, b in zip(*outs))
+            return outs[0]
+        finally:
+            cgs_lib.cgs_debug_set_flags(old)
+
+    plain = run(536870912, False)
+    for flags, graph in ((0, False), (0, True), (32768, True)):
+        assert all(torch.equal(a, b) for a, b in zip(run(flags, graph), plain)), (flags, graph)
