@@ -78,7 +78,7 @@ struct Cfg {
   // CG = 2: the CTA is one of a PAIR (cluster of two, tcgen05 cta_group::2, M = 256): each CTA loads its own M tile
   // and HALF the rows of every weight atom; the leader's MMAs read both halves.  Per CTA a stage is 16 KB of A plus
   // half the weights, so the ring is 6 stages deep where single CTAs get 4 (the load latency of ~1-2 k cycles is what
-  // the 4-stage ring does not cover, profiles/round2_ncu_summary.md D1), and L2 delivers each weight byte once per pair.
+  // the 4-stage ring does not cover, profiles/round2_ncu_summary.md D2), and L2 delivers each weight byte once per pair.
   static constexpr int KB = (NS > 1 || MT > 1 || BN >= 256 || CG > 1) ? 1 : 2;
   static constexpr int B_ATOM_BYTES = BN * BK * 4 / CG;          // per CTA
   static constexpr int A_STAGE_BYTES = (MT > 1 ? MT : KB) * A_ATOM_BYTES;
