@@ -114,10 +114,28 @@ class Refiner():
                                                      ws.numel(), L.stream_ptr()))
         return img[..., :self._cimg], logit
 
+    def prefetch(self, fake_feature):
+        """Start the host-to-device copy of the NEXT proposal batch on a side stream and return the device tensor to
+        hand to `build_refiner` later: the upload then overlaps the refinement of the current batch (the fill-up loop
+        knows its next proposals one batch ahead).  `fake_feature`: numpy array or (ideally pinned) host tensor."""
+        dev = self._spec.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            t, _ = R.to_device(fake_feature, torch.float32, dev)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        t._cgs_ready = ready                                     # build_refiner orders its stream after the copy
+        return t
+
     def build_refiner(self, fake_feature, real_batch=None, mode='deterministic', prob_indices=None,
                       keep_optimal_feature=False):
         if mode not in ('deterministic', 'probabilistic'):
             raise NotImplementedError(mode)
+        ready = getattr(fake_feature, "_cgs_ready", None)
+        if ready is not None:                                    # a batch staged by prefetch()
+            torch.cuda.current_stream().wait_event(ready)
+            fake_feature.record_stream(torch.cuda.current_stream())
         method = self.optimizer.method
         if method == 'ladam':
             # the reference calls apply_gradient without a loss here (collaborator.py:66) -> policy.py:51 fails

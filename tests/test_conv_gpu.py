@@ -460,3 +460,28 @@ def test_programmatic_dependent_launch_is_bit_identical_at_scale(cgs_lib, cuda_d
     plain = run(536870912, False)
     for flags, graph in ((0, False), (0, True), (32768, True)):
         assert all(torch.equal(a, b) for a, b in zip(run(flags, graph), plain)), (flags, graph)
+
+
+def test_prefetch_overlaps_upload_and_changes_nothing(cgs_lib, cuda_device):
+    """`Refiner.prefetch` uploads the next proposal batch on a side stream; `build_refiner` orders itself after the copy.
+    Same bits as handing the host array over directly, also when the prefetch is issued while another batch is being
+    refined and with graph replay."""
+    from cgs import nets as N
+    from sampling.collaborator import Refiner
+    arch, w, spec = _make("dcgan32_l1", 5, 2.5, cuda_device, "tf32")
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.relu(torch.randn(9, *arch["feature_shape"], generator=g)).pin_memory() for _ in range(3)]
+    for graph in (False, True):
+        r = Refiner(3, 0.1, cuda_graph=graph)
+        r.set_env(N.discriminator_spec(spec), N.feature_to_data_spec(spec), N.loss_refine)
+        direct = []
+        for h in batches:
+            x = r.build_refiner(h.numpy())
+            direct.append((torch.from_numpy(x), r.optimal_logit.clone().cpu()))
+        staged = r.prefetch(batches[0])
+        for i in range(3):
+            nxt = r.prefetch(batches[i + 1]) if i + 1 < 3 else None      # issued before batch i is refined
+            x = r.build_refiner(staged)
+            assert isinstance(x, torch.Tensor) and x.is_cuda
+            assert torch.equal(x.cpu(), direct[i][0]) and torch.equal(r.optimal_logit.cpu(), direct[i][1])
+            staged = nxt
