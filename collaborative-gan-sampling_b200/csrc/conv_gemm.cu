@@ -1042,6 +1042,13 @@ int validate(const ConvGemmParams& p, int w_cols) {
 
 }  // namespace
 
+int plan_fusion(ConvGemmParams& p) {
+  derive_act(p);
+  const int ns = fusion_slots(p, pick_bn(p.N));
+  if (ns) build_fusion(p, ns);
+  return ns;
+}
+
 int debug_trace_read(unsigned long long* out, int cap) {
   cudaDeviceSynchronize();
   const int n = cap < 32768 ? cap : 32768;

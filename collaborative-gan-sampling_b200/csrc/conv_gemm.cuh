@@ -223,5 +223,8 @@ __device__ __forceinline__ float4 epilogue4(const ConvGemmParams& p, int off, fl
 // host launchers (conv_gemm.cu)
 int launch_conv_gemm_tc(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream);
 int launch_conv_gemm_simt(const ConvGemmParams& p, const float* w, int w_rows, int w_cols, cudaStream_t stream);
+// host only: fills p.grp / p.shf the way the class-fused launch would and returns the slots per tile (0 = this pass
+// is never class-fused).  No device state is touched (cgs_debug_fusion_plan).
+int plan_fusion(ConvGemmParams& p);
 
 }  // namespace cgs

@@ -1456,6 +1456,42 @@ extern "C" int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* 
 // Host-only introspection (no GPU needed): the gathered-GEMM parameters a layer pass is lowered to, flattened to
 // int32 so tests can replay the exact gather on the CPU.  Layout: [IH, IW, Cs, cblocks, MH, MW, S, M, OH, OW, ON,
 // os, N, nclasses, window, win_k, win_x0, in_pitch_px] then per class [k0, nkb, ntaps, oy0, ox0, dy[32], dx[32]].  Returns the number of ints.
+// Host-only introspection of the class-fused lowering (include/cgs.h).
+extern "C" int64_t cgs_debug_fusion_plan(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out, int64_t capacity) {
+  if (!L) return set_error(CGS_ERR_INVALID, "null layer");
+  if (use_window(*L, backward != 0) || use_scatter(*L, backward != 0)) return 0;
+  ConvGemmParams p;
+  int rc = backward ? make_backward_params(*L, B, nullptr, nullptr, p) : make_forward_params(*L, B, nullptr, nullptr, p);
+  if (rc) return rc;
+  const int ns = plan_fusion(p);
+  if (!ns) return 0;
+  int nshf = 0;
+  for (int g = 0; g < p.ngroups; ++g) nshf += p.grp[g].nshifts;
+  const int64_t need = 2 + (int64_t)p.ngroups * 7 + (int64_t)nshf * 48;
+  if (!out) return need;
+  if (capacity < need) return set_error(CGS_ERR_INVALID, "capacity too small");
+  int32_t* o = out;
+  *o++ = ns; *o++ = p.ngroups;
+  for (int g = 0; g < p.ngroups; ++g) {
+    const FuseGroup& G = p.grp[g];
+    *o++ = G.nshifts; *o++ = G.shift0; *o++ = G.ncls;
+    for (int q = 0; q < 4; ++q) *o++ = G.cls[q];
+  }
+  for (int i = 0; i < nshf; ++i) {
+    const FuseShift& s = p.shf[i];
+    *o++ = s.dy; *o++ = s.dx; *o++ = s.ncls; *o++ = s.nrun;
+    for (int q = 0; q < 4; ++q) *o++ = s.slot[q];
+    for (int q = 0; q < 4; ++q) *o++ = s.katom0[q];
+    for (int q = 0; q < 4; ++q) *o++ = s.run_slot[q];
+    for (int q = 0; q < 4; ++q) *o++ = s.run_len[q];
+    for (int q = 0; q < 4; ++q) *o++ = s.run_acc[q];
+    for (int r = 0; r < 2; ++r) for (int q = 0; q < 4; ++q) *o++ = s.pc_slot[r][q];
+    for (int r = 0; r < 2; ++r) for (int q = 0; q < 4; ++q) *o++ = s.pc_half[r][q];
+    for (int r = 0; r < 2; ++r) for (int q = 0; q < 4; ++q) *o++ = s.pc_katom[r][q];
+  }
+  return need;
+}
+
 extern "C" int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
                                          int64_t capacity) {
   if (!L) return set_error(CGS_ERR_INVALID, "null layer");

@@ -224,6 +224,13 @@ CGS_API int64_t cgs_pack_map(const cgs_layer_desc* L, int backward, int32_t* ky,
 CGS_API int64_t cgs_debug_gemm_params(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out,
                                       int64_t capacity);
 
+/* Host-only introspection of the class-fused lowering of a transposed-type pass (csrc/conv_gemm.cuh FuseShift /
+ * FuseGroup): returns 0 when the pass is never class-fused, else writes [slots per tile, ngroups] + per group [nshifts,
+ * shift0, ncls, cls[4]] + per shift [dy, dx, ncls, nrun, slot[4], katom0[4], run_slot[4], run_len[4], run_acc[4],
+ * pc_slot[2][4], pc_half[2][4], pc_katom[2][4]] (the pc_* tables are the per-CTA-rank half-atom boxes of a CTA pair).
+ * NULL `out` queries the length.  Lets tests check the fused walk and the pair split on the CPU. */
+CGS_API int64_t cgs_debug_fusion_plan(const cgs_layer_desc* L, int backward, int64_t B, int32_t* out, int64_t capacity);
+
 /* Lowering of a pass: 0 = gather layout (K order given by cgs_pack_map), 1 = scatter layout, 2 = window layout
  * (strided passes reading a <= 4-channel image: rows = large channel, K index = ky*32 + kx*4 + small channel).  Transposed-type
  * passes with <= 4 output channels (deconv -> image forward, first-conv data-gradient) run as one GEMM over the

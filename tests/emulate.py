@@ -130,3 +130,28 @@ def layer_pass(layer, backward, B, x_padded, w_packed):
         col = replay(p, np.asarray(x_padded, np.float64).reshape(p["M"], 1, 1, p["Cs"]), w_packed, p["M"])
         return col2im(col.reshape(p["M"], p["ON"]), layer, backward, B)
     return replay(p, x_padded, w_packed, B)
+
+
+def fusion_plan(layer, backward, B):
+    """Decoded cgs_debug_fusion_plan (None when the pass is never class-fused)."""
+    lib = L.load()
+    d = N._layer_desc(layer)
+    n = L.check(lib.cgs_debug_fusion_plan(C.byref(d), int(backward), B, None, 0))
+    if n == 0:
+        return None
+    buf = np.zeros(n, np.int32)
+    L.check(lib.cgs_debug_fusion_plan(C.byref(d), int(backward), B, buf.ctypes.data, n))
+    v = buf.tolist()
+    plan = dict(ns=v[0], groups=[], shifts=[])
+    off = 2
+    for _ in range(v[1]):
+        plan["groups"].append(dict(nshifts=v[off], shift0=v[off + 1], ncls=v[off + 2], cls=v[off + 3:off + 7]))
+        off += 7
+    nshf = sum(g["nshifts"] for g in plan["groups"])
+    for _ in range(nshf):
+        s = v[off:off + 48]
+        plan["shifts"].append(dict(dy=s[0], dx=s[1], ncls=s[2], nrun=s[3], slot=s[4:8], katom0=s[8:12], run_slot=s[12:16],
+                                   run_len=s[16:20], run_acc=s[20:24], pc_slot=[s[24:28], s[28:32]],
+                                   pc_half=[s[32:36], s[36:40]], pc_katom=[s[40:44], s[44:48]]))
+        off += 48
+    return plan

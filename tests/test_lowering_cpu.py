@@ -76,3 +76,74 @@ def test_multiply_high_division_is_exact():
                 continue
             got = n if magic == 0 else (n * magic) >> 64
             assert got == n // d, (n, d)
+
+
+@pytest.mark.parametrize("arch_name", ["dcgan32_l1", "dcgan64_l1", "mnist"])
+def test_class_fusion_plan_and_cta_pair_split(cgs_lib, arch_name):
+    """Host logic of the class-fused tiles and of their split over a CTA pair (csrc/conv_gemm.cu build_fusion), checked
+    without a GPU: every (class, tap) of a group appears exactly once, at the shift of its tap and with the K atom the
+    weight packing gave it; each class meets its taps in packing order (so fused and one-class tiles accumulate in the
+    same order); runs are adjacent slots with one accumulate state and at most 256 columns; the two CTAs of a pair
+    fetch complementary halves of every run, each exactly once, into distinct half-atom slots."""
+    from cgs import nets as N
+    arch = N.get_arch(arch_name)
+    fused = 0
+    for layer in arch["gtail"] + arch["d"][:-1]:
+        for backward in (False, True):
+            plan = emulate.fusion_plan(layer, backward, 4)
+            p = emulate.gemm_params(layer, backward, 4)
+            transposed = p["os"] == 2 and p["nclasses"] == 4 and p["cblocks"] > 0 and not p["window"]
+            if plan is None:
+                # only k = 5 transposed-type passes with N <= 128 are ever fused
+                assert not (transposed and layer["k"] == 5 and p["N"] <= 128), layer["name"]
+                continue
+            fused += 1
+            assert transposed and layer["k"] == 5
+            cb = p["cblocks"]
+            assert plan["ns"] == (4 if p["N"] <= 64 else 2) and len(plan["groups"]) == (1 if plan["ns"] == 4 else 2)
+            seen_classes = []
+            for G in plan["groups"]:
+                cls = G["cls"][:G["ncls"]]
+                assert G["ncls"] == plan["ns"]
+                seen_classes += cls
+                if plan["ns"] == 2:
+                    assert p["cls"][cls[0]]["oy0"] % 2 == p["cls"][cls[1]]["oy0"] % 2
+                shifts = plan["shifts"][G["shift0"]:G["shift0"] + G["nshifts"]]
+                assert len({(s["dy"], s["dx"]) for s in shifts}) == len(shifts)
+                covered = {c: [] for c in cls}          # class -> K atoms in the order of the walk
+                touched = set()
+                for s in shifts:
+                    n = s["ncls"]
+                    slots = s["slot"][:n]
+                    assert slots == sorted(set(slots)) and 1 <= n <= G["ncls"]
+                    for q, slot in enumerate(slots):
+                        g = p["cls"][cls[slot]]
+                        taps = [t for t in range(g["ntaps"]) if (g["dy"][t], g["dx"][t]) == (s["dy"], s["dx"])]
+                        assert len(taps) == 1, (layer["name"], s["dy"], s["dx"])
+                        assert s["katom0"][q] == (g["k0"] + taps[0] * cb * 32) // 32
+                        covered[cls[slot]].append(s["katom0"][q])
+                    # runs: a partition of the listed slots into ranges of adjacent slots with one accumulate state
+                    i = 0
+                    for r in range(s["nrun"]):
+                        s0, ln = s["run_slot"][r], s["run_len"][r]
+                        assert slots[i:i + ln] == list(range(s0, s0 + ln)) and ln * p["N"] <= 256
+                        assert {slot in touched for slot in slots[i:i + ln]} == {bool(s["run_acc"][r])}
+                        # CTA pair: the run's B rows are its atoms back to back, split in the middle
+                        pieces = [(i + j // 2, j % 2) for j in range(2 * ln)]          # (entry, half)
+                        for rank in (0, 1):
+                            mine = pieces[rank * ln:(rank + 1) * ln]
+                            got = [(s["pc_slot"][rank][i + j], s["pc_half"][rank][i + j], s["pc_katom"][rank][i + j])
+                                   for j in range(ln)]
+                            assert got == [(s0 + j, half, s["katom0"][e]) for j, (e, half) in enumerate(mine)]
+                        i += ln
+                    assert i == n
+                    for rank in (0, 1):
+                        assert len(set(s["pc_slot"][rank][:n])) == n            # distinct half-atom slots per CTA
+                    both = sorted((s["pc_katom"][r][q], s["pc_half"][r][q]) for r in (0, 1) for q in range(n))
+                    assert both == sorted((k, h) for k in s["katom0"][:n] for h in (0, 1))
+                    touched |= set(slots)
+                for c in cls:
+                    g = p["cls"][c]
+                    assert covered[c] == [g["k0"] // 32 + t * cb for t in range(g["ntaps"])], (layer["name"], c)
+            assert sorted(seen_classes) == [0, 1, 2, 3]
+    assert (fused > 0) == (arch_name != "mnist")
