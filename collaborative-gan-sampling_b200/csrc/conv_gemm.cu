@@ -916,9 +916,40 @@ int fusion_slots(const ConvGemmParams& p, int bn) {
   return 0;
 }
 
+// Can a cluster of two CTAs of this kernel instance be resident on the current device (asked once per instance and
+// device)?  On a whole B200 the answer is always yes (148 = 2 x 74 TPCs); on a partitioned or otherwise restricted
+// device the launcher falls back to the single-CTA instance, which computes the same bits.
+template <typename K>
+bool cluster_pair_fits(K kernel, size_t smem, int threads) {
+  static std::atomic<int> state[kMaxDevices];          // 0 unknown, 1 fits, -1 does not
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  int st = state[dev].load(std::memory_order_acquire);
+  if (st == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    st = (e == cudaSuccess && n >= 1) ? 1 : -1;
+    state[dev].store(st, std::memory_order_release);
+  }
+  return st > 0;
+}
+
 template <int BN, int EPI, int NS = 1, int MT = 1, int CG = 1>
 int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cudaStream_t stream) {
   using C = Cfg<BN, NS, MT, CG>;
+  const ConvGemmParams p_in = p;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(CGS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmap;
@@ -983,6 +1014,8 @@ int launch_tc_epi(ConvGemmParams p, const float* w, int w_rows, int w_cols, cuda
     cudaError_t e = ensure_dyn_smem(conv_gemm_tc_kernel<BN, EPI, NS, MT, CG>, (size_t)C::SMEM_BYTES, smem_cache);
     if (e != cudaSuccess) return set_error(CGS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
+  if (CG > 1 && !cluster_pair_fits(conv_gemm_tc_kernel<BN, EPI, NS, MT, CG>, (size_t)C::SMEM_BYTES, kThreads))
+    return launch_tc_epi<BN, EPI, NS, MT, 1>(p_in, w, w_rows, w_cols, stream);
   if (NS > 1) build_fusion(p, NS); else p.fuse = 0;
   p.m2 = MT * CG;                             // adjacent M tiles per scheduling unit
   const int m_units = (p.m_tiles + p.m2 - 1) / p.m2;
